@@ -1,0 +1,154 @@
+/* meshode_b200.h -- C-ABI of libmeshode_b200.so (sm_100a CUDA implementation of
+ * MeshODE's data-parallel hot path).
+ *
+ * Every entry point takes plain DEVICE pointers and sizes plus the CUDA stream
+ * to enqueue on (a cudaStream_t passed as void*; NULL = legacy default stream).
+ * Nothing here synchronises the host unless its comment says so.  All functions
+ * return 0 (MO_OK) or a negative MO_ERR_* code; mo_last_error() gives the text
+ * of the calling thread's last failure.  There is no CPU fallback: without a
+ * CUDA device every compute entry returns MO_ERR_CUDA.
+ *
+ * Each declaration cites the reference interface (relative to the MeshODE
+ * source tree) that it replaces.  Tensors of the reference API map to
+ * (pointer, row count) pairs: V = float32 [n,3] contiguous, F = int32 [m,3],
+ * E = int32 [e,2].
+ */
+#ifndef MESHODE_B200_H_
+#define MESHODE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mo_stream_t; /* cudaStream_t */
+
+enum {
+  MO_OK = 0,
+  MO_ERR_BAD_HANDLE = -1, /* param_id not created / already destroyed */
+  MO_ERR_BAD_ARG = -2,    /* null pointer, negative size, size mismatch with stored edges */
+  MO_ERR_CUDA = -3,       /* a CUDA runtime call failed (text in mo_last_error) */
+  MO_ERR_STATE = -4       /* edges of that kind were never stored for this template */
+};
+
+/* which edge set a template holds; one set per template, each Store* overwrites it
+ * (src/interface/rigid_layer.cc:29, graph_layer.cc:29, cad_layer.cc:33) */
+enum { MO_EDGES_NONE = -1, MO_EDGES_RIGID = 0, MO_EDGES_GRAPH = 1, MO_EDGES_CAD = 2 };
+
+int mo_version(void);
+const char* mo_last_error(void);
+/* number of visible CUDA devices (0 when there is none). */
+int mo_device_count(void);
+
+/* ---- template = DeformParams (src/interface/deform_params.h:7-25) ------------ */
+
+/* InitializeDeformTemplate(tensorV, tensorF, symmetry, grid_resolution) -> param_id
+ * (src/interface/deform_params.cc:16-40): CopyTensorToMesh(normalize=1)
+ * (src/interface/mesh_tensor.cc:47-85) + Mesh::Normalize (src/lib/mesh.cc:66-85) +
+ * Mesh::ConstructDistanceField (src/lib/mesh.cc:106-152).  `symmetry` is accepted and
+ * ignored, as in the reference (the reflection runs on a still-empty mesh, :28-33).
+ * The distance field, nearest-triangle index, scale and translation stay on the
+ * device; no host synchronisation. */
+int mo_template_create(const float* d_V, int nV, const int* d_F, int nF, int symmetry, int grid_res,
+                       mo_stream_t stream, int* out_param_id);
+
+/* Same, but only voxel slices z in [z0, z1) are computed (z-slab sharding of one large
+ * grid across GPUs); the other slices hold 1e30 (src/lib/uniformgrid.cc:9-17 initial
+ * value) until the caller fills them, e.g. by an all-gather on the pointers returned
+ * by mo_template_grid(). */
+int mo_template_create_slab(const float* d_V, int nV, const int* d_F, int nF, int grid_res, int z0, int z1,
+                            mo_stream_t stream, int* out_param_id);
+
+/* Mesh::ConstructDistanceField on an ALREADY normalised FP64 mesh (the C++ drivers'
+ * path: ref.Normalize(); ref.ConstructDistanceField(grid) -- src/app/rigid_deform.cc:49-52).
+ * scale/trans are recorded as given (Mesh::GetScale/GetTranslation). */
+int mo_template_create_normalized(const double* d_Vn, int nV, const int* d_F, int nF, int grid_res, double scale,
+                                  const double* h_trans3, mo_stream_t stream, int* out_param_id);
+
+/* g_params entries are never freed in the reference (deform_params.cc:7-14); this is additive. */
+int mo_template_destroy(int param_id);
+
+/* Host copies of the template's metadata (Mesh::GetScale / GetTranslation,
+ * UniformGrid::Dimension).  Synchronises `stream`.  Any out pointer may be NULL. */
+int mo_template_info(int param_id, mo_stream_t stream, int* grid_res, int* nV, int* nF, double* scale,
+                     double* trans3);
+
+/* Device pointers of the stored fields, all N^3 in [z][y][x] order
+ * (UniformGrid::GetDistance(i=z, j=y, k=x), src/lib/uniformgrid.h:29-31):
+ *   grid_f64  : sqrt of the FP64 squared distance, what UniformGrid stores;
+ *   grid_f32  : (float)grid_f64, the value DistanceFloat<> fetches (uniformgrid.cc:122);
+ *   nearest   : index into F of the nearest triangle (igl's `I`, src/lib/mesh.cc:138-140),
+ *               lowest index on exact FP64 ties.
+ * Any out pointer may be NULL. */
+int mo_template_grid(int param_id, const double** d_grid_f64, const float** d_grid_f32, const int** d_nearest);
+
+/* Copies voxel slices z in [z0, z1) between the template's fields and caller-owned full-size
+ * (N^3) device arrays laid out the same way: direction 0 = template -> caller (read back,
+ * e.g. into torch tensors), 1 = caller -> template (e.g. after an all-gather of z-slabs).
+ * Any of the three array pointers may be NULL. Asynchronous on `stream`. */
+int mo_template_copy_grid(int param_id, int direction, int z0, int z1, double* d_grid_f64, float* d_grid_f32,
+                          int* d_nearest, mo_stream_t stream);
+
+/* Device pointer of the normalised FP64 target vertices [nV,3] (Mesh::GetV after Normalize). */
+int mo_template_vertices(int param_id, const double** d_Vn);
+
+/* Build statistics of the last grid build of this template (for roofline accounting):
+ * point-triangle tests executed in FP32, exact FP64 re-evaluations, candidate-cull tests.
+ * Synchronises `stream`. */
+int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long* fp32_tests,
+                            unsigned long long* fp64_tests, unsigned long long* cull_tests);
+
+/* ---- NormalizeByTemplate / DenormalizeByTemplate (src/interface/normalize.cc:5-45) ---- */
+/* in place on float32 [n,3]; inverse = 0: (v - trans)/scale, inverse = 1: v*scale + trans,
+ * arithmetic in FP64 rounded once to float32 as in the reference. */
+int mo_normalize_by_template(float* d_V, int n, int param_id, int inverse, mo_stream_t stream);
+
+/* ---- DistanceFieldLoss (src/interface/distance_layer.cc) ---------------------------- */
+/* DistanceFieldLoss_forward (:8-37): out[i] = DistanceFloat<float>(V[i])^2, float32 [n]. */
+int mo_distance_forward(const float* d_V, int n, int param_id, float* d_out, mo_stream_t stream);
+/* DistanceFieldLoss_backward (:39-81): out[i,:] = 0.5 * d(dist^2)/dV[i] via Jet<float,3>
+ * arithmetic, float32 [n,3]. */
+int mo_distance_backward(const float* d_V, int n, int param_id, float* d_grad, mo_stream_t stream);
+/* both in one pass over V (additive; 28 B of HBM traffic per vertex instead of 16 + 24). */
+int mo_distance_forward_backward(const float* d_V, int n, int param_id, float* d_out, float* d_grad,
+                                 mo_stream_t stream);
+/* UniformGrid::distance<double> / distance<Jet<double,3>> (src/lib/uniformgrid.cc:18-83), the
+ * sampler behind DistanceLoss (src/lib/distanceloss.h:6-25): val [n] and, if d_grad != NULL,
+ * the three partials [n,3]. */
+int mo_distance_f64(const double* d_P, int n, int param_id, double* d_val, double* d_grad, mo_stream_t stream);
+
+/* ---- edge rigidity (src/interface/{rigid,graph,cad}_layer.cc) ----------------------- */
+/* Store{Rigidity,Graph,Cad}Information: rest vectors (and CAD lambda) from the current V.
+ * kind RIGID uses F (3*nF directed face edges), GRAPH uses E, CAD uses E rows then face edges.
+ * Unused index arrays may be NULL with count 0.  Also captures the connectivity for the
+ * deterministic backward. */
+int mo_edges_store(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
+                   int nE, mo_stream_t stream);
+/* {Rigid,Graph,Cad}EdgeLoss_forward: out float32 [nEdges,3], nEdges = 3nF | nE | nE+3nF.
+ * Reads the index arrays passed here, like the reference. */
+int mo_edges_forward(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
+                     int nE, float* d_out, mo_stream_t stream);
+/* {Rigid,Graph,Cad}EdgeLoss_backward: out float32 [nV,3].  Vertex-gather over the CSR built
+ * by mo_edges_store, accumulating each vertex's incident edges in edge order, so the result
+ * is bit-identical to the reference's serial scatter loop.  The counts must equal the
+ * stored ones (MO_ERR_BAD_ARG otherwise). */
+int mo_edges_backward(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
+                      int nE, float* d_grad, mo_stream_t stream);
+/* Same result up to float32 summation order: edge-parallel scatter with warp-aggregated
+ * red.global.add.f32 on the index arrays passed here.  d_grad is zeroed first. */
+int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF,
+                             const int* d_E, int nE, float* d_grad, mo_stream_t stream);
+
+/* ---- fused per-iteration loss (src/python/layers/*_loss_layer.py) --------------------- */
+/* L = 0.5*sum(dist_fwd) + w_edge*0.5*sum(edge_fwd);  grad = mask*dist_bwd + w_edge*edge_bwd
+ * (rigid_loss_layer.py:9-27 with w_edge = 1; graph_loss_layer.py:11-43 with w_edge =
+ * rigidity^2 and mask_threshold = 0.5*0.03^2 on 0.5*dist_fwd; mask_threshold <= 0 disables
+ * the mask).  dist_param_id selects the distance field, edge_param_id the stored edges
+ * (graph_loss2_layer.py:18-19 uses two different templates).  d_loss receives one double
+ * (sum accumulated in FP64); d_grad float32 [nV,3]. Either may be NULL. */
+int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* d_V, int nV, float w_edge,
+                             float mask_threshold, double* d_loss, float* d_grad, mo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHODE_B200_H_ */

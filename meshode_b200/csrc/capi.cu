@@ -1,0 +1,341 @@
+// C-ABI of libmeshode_b200.so: the handle table that replaces the reference's global
+// g_params vector (src/interface/deform_params.cc:7-14) and the thin entry points declared
+// in include/meshode_b200.h.
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mo {
+
+static thread_local std::string t_error;
+void set_error(const std::string& s) { t_error = s; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  t_error = buf;
+  cudaGetLastError();   // clear the sticky flag of non-fatal errors
+  return MO_ERR_CUDA;
+}
+
+namespace {
+
+std::mutex g_mutex;
+std::vector<std::unique_ptr<Template>> g_templates;   // index = param_id, like g_params
+
+Template* lookup(int pid) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (pid < 0 || pid >= (int)g_templates.size() || !g_templates[pid]) {
+    set_error("bad param_id " + std::to_string(pid));
+    return nullptr;
+  }
+  return g_templates[pid].get();
+}
+
+void release(Template& T) {
+  free_edges(T);
+  cudaFree(T.d_Vn); cudaFree(T.d_F); cudaFree(T.d_grid64); cudaFree(T.d_grid32); cudaFree(T.d_nearest);
+  cudaFree(T.d_xf); cudaFree(T.d_stats);
+}
+
+int allocate(Template& T) {
+  const size_t nvox = (size_t)T.N * T.N * T.N;
+  MO_CUDA(cudaGetDevice(&T.device));
+  MO_CUDA(cudaMalloc(&T.d_Vn, sizeof(double) * 3 * (size_t)T.nV));
+  MO_CUDA(cudaMalloc(&T.d_F, sizeof(int) * 3 * (size_t)T.nF));
+  MO_CUDA(cudaMalloc(&T.d_grid64, sizeof(double) * nvox));
+  MO_CUDA(cudaMalloc(&T.d_grid32, sizeof(float) * nvox));
+  MO_CUDA(cudaMalloc(&T.d_nearest, sizeof(int) * nvox));
+  MO_CUDA(cudaMalloc(&T.d_xf, sizeof(double) * 4));
+  MO_CUDA(cudaMalloc(&T.d_stats, sizeof(unsigned long long) * 4));
+  return MO_OK;
+}
+
+int publish(std::unique_ptr<Template>& T, int* out) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_templates.push_back(std::move(T));
+  *out = (int)g_templates.size() - 1;
+  return MO_OK;
+}
+
+int create_common(const float* d_V, const double* d_Vn, int nV, const int* d_F, int nF, int N, int z0, int z1, double scale,
+                  const double* h_trans, cudaStream_t s, int* out) {
+  MO_REQUIRE(out != nullptr, "out_param_id is null");
+  MO_REQUIRE((d_V != nullptr || d_Vn != nullptr) && d_F != nullptr, "null vertex / face pointer");
+  MO_REQUIRE(nV > 0 && nF > 0, "empty mesh");
+  MO_REQUIRE(N >= 2 && N <= 1024, "grid_resolution must be in [2, 1024]");
+  MO_REQUIRE(0 <= z0 && z0 < z1 && z1 <= N, "bad z-slab");
+  std::unique_ptr<Template> T(new Template());
+  T->N = N; T->nV = nV; T->nF = nF; T->z0 = z0; T->z1 = z1;
+  int rc = allocate(*T);
+  if (rc != MO_OK) { release(*T); return rc; }
+  cudaError_t e = cudaMemcpyAsync(T->d_F, d_F, sizeof(int) * 3 * (size_t)nF, cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess && d_Vn) {
+    e = cudaMemcpyAsync(T->d_Vn, d_Vn, sizeof(double) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, s);
+    const double xf[4] = {scale, h_trans ? h_trans[0] : 0.0, h_trans ? h_trans[1] : 0.0, h_trans ? h_trans[2] : 0.0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(T->d_xf, xf, sizeof(xf), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // xf lives on this frame
+  }
+  if (e != cudaSuccess) { release(*T); return cuda_fail(e, "template upload", __FILE__, __LINE__); }
+  rc = d_Vn ? build_field_from_normalized(*T, s) : build_field_from_f32(*T, d_V, s);
+  if (rc != MO_OK) { release(*T); return rc; }
+  return publish(T, out);
+}
+
+}  // namespace
+}  // namespace mo
+
+namespace mo {
+__global__ void k_normalize(float* __restrict__ V, int n3, const double* __restrict__ xf, int inverse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n3) return;
+  const double scale = xf[0], t = xf[1 + i % 3];
+  const double v = (double)V[i];
+  // normalize.cc:21 : (v - trans)/scale ; normalize.cc:42 : v*scale + trans   (FP64, rounded once)
+  V[i] = inverse ? (float)dadd(dmul(v, scale), t) : (float)__ddiv_rn(dsub(v, t), scale);
+}
+}  // namespace mo
+
+using namespace mo;
+
+extern "C" {
+
+int mo_version(void) { return 1; }
+const char* mo_last_error(void) { return t_error.c_str(); }
+int mo_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int mo_template_create(const float* d_V, int nV, const int* d_F, int nF, int symmetry, int grid_res, mo_stream_t stream,
+                       int* out_param_id) {
+  (void)symmetry;   // no-op in the reference: deform_params.cc:28-33
+  return create_common(d_V, nullptr, nV, d_F, nF, grid_res, 0, grid_res, 1.0, nullptr, (cudaStream_t)stream, out_param_id);
+}
+
+int mo_template_create_slab(const float* d_V, int nV, const int* d_F, int nF, int grid_res, int z0, int z1,
+                            mo_stream_t stream, int* out_param_id) {
+  return create_common(d_V, nullptr, nV, d_F, nF, grid_res, z0, z1, 1.0, nullptr, (cudaStream_t)stream, out_param_id);
+}
+
+int mo_template_create_normalized(const double* d_Vn, int nV, const int* d_F, int nF, int grid_res, double scale,
+                                  const double* h_trans3, mo_stream_t stream, int* out_param_id) {
+  return create_common(nullptr, d_Vn, nV, d_F, nF, grid_res, 0, grid_res, scale, h_trans3, (cudaStream_t)stream, out_param_id);
+}
+
+int mo_template_destroy(int param_id) {
+  std::unique_ptr<Template> T;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (param_id < 0 || param_id >= (int)g_templates.size() || !g_templates[param_id]) {
+      set_error("bad param_id " + std::to_string(param_id));
+      return MO_ERR_BAD_HANDLE;
+    }
+    T = std::move(g_templates[param_id]);
+  }
+  cudaDeviceSynchronize();
+  release(*T);
+  return MO_OK;
+}
+
+int mo_template_info(int param_id, mo_stream_t stream, int* grid_res, int* nV, int* nF, double* scale, double* trans3) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  if (grid_res) *grid_res = T->N;
+  if (nV) *nV = T->nV;
+  if (nF) *nF = T->nF;
+  if (scale || trans3) {
+    double xf[4];
+    MO_CUDA(cudaMemcpyAsync(xf, T->d_xf, sizeof(xf), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (scale) *scale = xf[0];
+    if (trans3) { trans3[0] = xf[1]; trans3[1] = xf[2]; trans3[2] = xf[3]; }
+  }
+  return MO_OK;
+}
+
+int mo_template_grid(int param_id, const double** d_grid_f64, const float** d_grid_f32, const int** d_nearest) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  if (d_grid_f64) *d_grid_f64 = T->d_grid64;
+  if (d_grid_f32) *d_grid_f32 = T->d_grid32;
+  if (d_nearest) *d_nearest = T->d_nearest;
+  return MO_OK;
+}
+
+int mo_template_copy_grid(int param_id, int direction, int z0, int z1, double* d_grid_f64, float* d_grid_f32,
+                          int* d_nearest, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  MO_REQUIRE(0 <= z0 && z0 <= z1 && z1 <= T->N, "bad slice range");
+  MO_REQUIRE(direction == 0 || direction == 1, "direction must be 0 or 1");
+  const size_t off = (size_t)z0 * T->N * T->N, cnt = (size_t)(z1 - z0) * T->N * T->N;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cnt == 0) return MO_OK;
+  if (d_grid_f64)
+    MO_CUDA(cudaMemcpyAsync(direction ? (void*)(T->d_grid64 + off) : (void*)(d_grid_f64 + off),
+                            direction ? (const void*)(d_grid_f64 + off) : (const void*)(T->d_grid64 + off),
+                            cnt * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (d_grid_f32)
+    MO_CUDA(cudaMemcpyAsync(direction ? (void*)(T->d_grid32 + off) : (void*)(d_grid_f32 + off),
+                            direction ? (const void*)(d_grid_f32 + off) : (const void*)(T->d_grid32 + off),
+                            cnt * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (d_nearest)
+    MO_CUDA(cudaMemcpyAsync(direction ? (void*)(T->d_nearest + off) : (void*)(d_nearest + off),
+                            direction ? (const void*)(d_nearest + off) : (const void*)(T->d_nearest + off),
+                            cnt * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return MO_OK;
+}
+
+int mo_template_vertices(int param_id, const double** d_Vn) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  if (d_Vn) *d_Vn = T->d_Vn;
+  return MO_OK;
+}
+
+int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long* fp32_tests, unsigned long long* fp64_tests,
+                            unsigned long long* cull_tests) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  unsigned long long h[4];
+  MO_CUDA(cudaMemcpyAsync(h, T->d_stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  MO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (fp32_tests) *fp32_tests = h[0];
+  if (fp64_tests) *fp64_tests = h[1];
+  if (cull_tests) *cull_tests = h[2];
+  if (h[3]) {
+    set_error("template holds invalid input: " + std::string((h[3] & 1) ? "[face index out of range] " : "") +
+              ((h[3] & 2) ? "[non-finite vertex] " : "") + ((h[3] & 4) ? "[edge index out of range]" : ""));
+    return MO_ERR_BAD_ARG;
+  }
+  return MO_OK;
+}
+
+int mo_distance_forward(const float* d_V, int n, int param_id, float* d_out, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  MO_REQUIRE(n >= 0 && (n == 0 || (d_V && d_out)), "null pointer");
+  return launch_distance_f32(*T, d_V, n, d_out, nullptr, 1, (cudaStream_t)stream);
+}
+
+int mo_distance_backward(const float* d_V, int n, int param_id, float* d_grad, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  MO_REQUIRE(n >= 0 && (n == 0 || (d_V && d_grad)), "null pointer");
+  return launch_distance_f32(*T, d_V, n, nullptr, d_grad, 2, (cudaStream_t)stream);
+}
+
+int mo_distance_forward_backward(const float* d_V, int n, int param_id, float* d_out, float* d_grad, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  MO_REQUIRE(n >= 0 && (n == 0 || (d_V && d_out && d_grad)), "null pointer");
+  return launch_distance_f32(*T, d_V, n, d_out, d_grad, 3, (cudaStream_t)stream);
+}
+
+int mo_distance_f64(const double* d_P, int n, int param_id, double* d_val, double* d_grad, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  MO_REQUIRE(n >= 0 && (n == 0 || (d_P && d_val)), "null pointer");
+  return launch_distance_f64(*T, d_P, n, d_val, d_grad, (cudaStream_t)stream);
+}
+
+static int check_edge_args(int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE) {
+  MO_REQUIRE(kind == MO_EDGES_RIGID || kind == MO_EDGES_GRAPH || kind == MO_EDGES_CAD, "unknown edge kind");
+  MO_REQUIRE(nV >= 0 && nF >= 0 && nE >= 0, "negative size");
+  MO_REQUIRE(nV == 0 || d_V, "null vertex pointer");
+  MO_REQUIRE(kind == MO_EDGES_GRAPH || nF == 0 || d_F, "null face pointer");
+  MO_REQUIRE(kind == MO_EDGES_RIGID || nE == 0 || d_E, "null edge pointer");
+  return MO_OK;
+}
+
+static void canon(int kind, int& nF, int& nE) {
+  if (kind == MO_EDGES_RIGID) nE = 0;
+  if (kind == MO_EDGES_GRAPH) nF = 0;
+}
+
+int mo_edges_store(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
+                   mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
+  if (rc != MO_OK) return rc;
+  canon(kind, nF, nE);
+  return edges_store(*T, kind, d_V, nV, d_F, nF, d_E, nE, (cudaStream_t)stream);
+}
+
+static int check_stored(const Template& T, int kind, int nV, int nF, int nE, bool need_csr) {
+  if (T.kind != kind) { set_error("edges of this kind were not stored for this template"); return MO_ERR_STATE; }
+  MO_REQUIRE(nF == T.eF && nE == T.eE, "edge counts differ from the stored ones");
+  MO_REQUIRE(!need_csr || nV == T.eV, "vertex count differs from the stored one");
+  return MO_OK;
+}
+
+int mo_edges_forward(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
+                     float* d_out, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
+  if (rc != MO_OK) return rc;
+  canon(kind, nF, nE);
+  rc = check_stored(*T, kind, nV, nF, nE, false);
+  if (rc != MO_OK) return rc;
+  MO_REQUIRE(T->nEdges == 0 || d_out, "null output pointer");
+  return edges_forward(*T, kind, d_V, nV, d_F, nF, d_E, nE, d_out, (cudaStream_t)stream);
+}
+
+int mo_edges_backward(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
+                      float* d_grad, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
+  if (rc != MO_OK) return rc;
+  canon(kind, nF, nE);
+  rc = check_stored(*T, kind, nV, nF, nE, true);
+  if (rc != MO_OK) return rc;
+  MO_REQUIRE(nV == 0 || d_grad, "null output pointer");
+  return edges_backward(*T, d_V, nV, d_grad, (cudaStream_t)stream);
+}
+
+int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
+                             int nE, float* d_grad, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
+  if (rc != MO_OK) return rc;
+  canon(kind, nF, nE);
+  rc = check_stored(*T, kind, nV, nF, nE, false);
+  if (rc != MO_OK) return rc;
+  MO_REQUIRE(nV == 0 || d_grad, "null output pointer");
+  return edges_backward_atomic(*T, kind, d_V, nV, d_F, nF, d_E, nE, d_grad, (cudaStream_t)stream);
+}
+
+int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* d_V, int nV, float w_edge,
+                             float mask_threshold, double* d_loss, float* d_grad, mo_stream_t stream) {
+  Template* TD = lookup(dist_param_id);
+  if (!TD) return MO_ERR_BAD_HANDLE;
+  Template* TE = nullptr;
+  if (edge_param_id >= 0) {
+    TE = lookup(edge_param_id);
+    if (!TE) return MO_ERR_BAD_HANDLE;
+    if (TE->kind == MO_EDGES_NONE) { set_error("no edges stored for edge_param_id"); return MO_ERR_STATE; }
+    MO_REQUIRE(nV == TE->eV, "vertex count differs from the stored one");
+  }
+  MO_REQUIRE(nV >= 0 && (nV == 0 || d_V), "null pointer");
+  return loss_fused(*TD, TE, d_V, nV, w_edge, mask_threshold, d_loss, d_grad, (cudaStream_t)stream);
+}
+
+
+int mo_normalize_by_template(float* d_V, int n, int param_id, int inverse, mo_stream_t stream) {
+  Template* T = lookup(param_id);
+  if (!T) return MO_ERR_BAD_HANDLE;
+  MO_REQUIRE(n >= 0 && (n == 0 || d_V), "null pointer");
+  if (n == 0) return MO_OK;
+  k_normalize<<<div_up(3LL * n, 256), 256, 0, (cudaStream_t)stream>>>(d_V, 3 * n, T->d_xf, inverse);
+  MO_LAUNCH_CHECK();
+  return MO_OK;
+}
+
+}  // extern "C"

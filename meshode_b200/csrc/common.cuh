@@ -1,0 +1,89 @@
+// Internal declarations shared by the translation units of libmeshode_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <algorithm>
+#include <cstdio>
+#include <string>
+
+#include "../../include/meshode_b200.h"
+
+namespace mo {
+
+// What DeformParams holds in the reference (src/interface/deform_params.h:7-25), as device buffers.
+struct Template {
+  int device = 0;
+  int N = 0, nV = 0, nF = 0;
+  int z0 = 0, z1 = 0;
+  double* d_Vn = nullptr;       // [nV,3] normalised FP64 target vertices (Mesh::V_ after Normalize)
+  int* d_F = nullptr;           // [nF,3]
+  double* d_grid64 = nullptr;   // [N^3] z,y,x  (UniformGrid::voxel_distance_)
+  float* d_grid32 = nullptr;    // [N^3] (float) of the above
+  int* d_nearest = nullptr;     // [N^3] nearest triangle (igl's I)
+  double* d_xf = nullptr;       // [4] scale, trans.x, trans.y, trans.z  (params.scale / params.trans)
+  unsigned long long* d_stats = nullptr;   // [4] fp32 tests, fp64 tests, cull tests, error bits
+  // one edge set per template (params.edge_offset / edge_lambda)
+  int kind = MO_EDGES_NONE;
+  int eV = 0, eF = 0, eE = 0, nEdges = 0;
+  int2* d_ev = nullptr;         // [nEdges] (v0, v1)
+  float* d_rest = nullptr;      // [nEdges,3]
+  float* d_lambda = nullptr;    // [nEdges] (CAD only)
+  int* d_csr_start = nullptr;   // [eV+1]
+  int* d_csr_key = nullptr;     // [2*nEdges] 2*edge + side, ascending per vertex
+};
+
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define MO_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return ::mo::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+#define MO_LAUNCH_CHECK() MO_CUDA(cudaGetLastError())
+#define MO_REQUIRE(cond, msg)                                                \
+  do {                                                                       \
+    if (!(cond)) { ::mo::set_error(std::string("bad argument: ") + msg); return MO_ERR_BAD_ARG; } \
+  } while (0)
+
+// sdf_build.cu
+int build_field_from_f32(Template& T, const float* d_V, cudaStream_t s);
+int build_field_from_normalized(Template& T, cudaStream_t s);
+// sampler.cu
+int launch_distance_f32(const Template& T, const float* d_V, int n, float* d_out, float* d_grad, int mode, cudaStream_t s);
+int launch_distance_f64(const Template& T, const double* d_P, int n, double* d_val, double* d_grad, cudaStream_t s);
+// edges.cu
+void free_edges(Template& T);
+int edges_store(Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
+                cudaStream_t s);
+int edges_forward(const Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
+                  float* d_out, cudaStream_t s);
+int edges_backward(const Template& T, const float* d_V, int nV, float* d_grad, cudaStream_t s);
+int edges_backward_atomic(const Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
+                          int nE, float* d_grad, cudaStream_t s);
+int loss_fused(const Template& TD, const Template* TE, const float* d_V, int nV, float w_edge, float mask_thr,
+               double* d_loss, float* d_grad, cudaStream_t s);
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// order-preserving float <-> uint maps for atomicMin/atomicMax
+__device__ __forceinline__ unsigned f2o(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(unsigned o) {
+  unsigned u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+
+// IEEE round-to-nearest FP64 arithmetic that nvcc will not contract into FMAs, so the
+// FP64 parts match the host oracle (g++ -ffp-contract=off) bit for bit.
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+}  // namespace mo

@@ -1,0 +1,340 @@
+// Edge-rigidity losses: Store{Rigidity,Graph,Cad}Information and
+// {Rigid,Graph,Cad}EdgeLoss_forward/backward (reference src/interface/rigid_layer.cc,
+// graph_layer.cc, cad_layer.cc), plus the fused per-iteration loss of the Python layers
+// (src/python/layers/{rigid,graph,graph2}_loss_layer.py).
+//
+// forward  : one thread per edge, indices as passed by the caller, vertex gathers from L2.
+// backward : one thread per vertex walking a CSR (vertex -> incident (edge, side) keys in
+//            ascending edge order) built at store time, so each vertex accumulates its
+//            contributions in exactly the order of the reference's serial scatter loop:
+//            atomic-free and bit-identical.  An edge-parallel variant with warp-aggregated
+//            red.global.add.f32 is provided for callers whose connectivity changes.
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
+#include "common.cuh"
+#include "sampler.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mo {
+namespace {
+
+constexpr int kBlock = 256;
+
+// endpoints of edge e in the reference's enumeration order
+__device__ __forceinline__ int2 edge_endpoints(int kind, int e, const int* __restrict__ F, const int* __restrict__ E, int nE) {
+  if (kind == MO_EDGES_GRAPH || (kind == MO_EDGES_CAD && e < nE)) return make_int2(__ldg(E + 2 * (size_t)e), __ldg(E + 2 * (size_t)e + 1));
+  const int o = kind == MO_EDGES_CAD ? e - nE : e;
+  const int f = o / 3, j = o - 3 * f;
+  return make_int2(__ldg(F + 3 * (size_t)f + j), __ldg(F + 3 * (size_t)f + (j + 1) % 3));   // rigid_layer.cc:34-35
+}
+
+__global__ void k_edges_store(int kind, const float* __restrict__ V, int nV, const int* __restrict__ F,
+                              const int* __restrict__ E, int nE, int nEdges, int2* __restrict__ ev,
+                              float* __restrict__ rest, float* __restrict__ lambda, int* __restrict__ deg,
+                              unsigned long long* __restrict__ stats) {
+  const int e = blockIdx.x * kBlock + threadIdx.x;
+  if (e >= nEdges) return;
+  int2 v = edge_endpoints(kind, e, F, E, nE);
+  if ((unsigned)v.x >= (unsigned)nV || (unsigned)v.y >= (unsigned)nV) {
+    atomicOr(&stats[3], 4ull);
+    ev[e] = make_int2(-1, -1);
+    rest[3 * (size_t)e] = rest[3 * (size_t)e + 1] = rest[3 * (size_t)e + 2] = 0.f;
+    if (lambda) lambda[e] = 0.f;
+    return;
+  }
+  ev[e] = v;
+  float r[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r[k] = fsub(__ldg(V + 3 * (size_t)v.y + k), __ldg(V + 3 * (size_t)v.x + k));   // rigid_layer.cc:39-43
+    rest[3 * (size_t)e + k] = r[k];
+  }
+  if (lambda) {   // cad_layer.cc:48-49: 2e-2 / (norm + 1e-8), double arithmetic, stored as float
+    const float norm = __fsqrt_rn(fadd(fadd(fmul(r[0], r[0]), fmul(r[1], r[1])), fmul(r[2], r[2])));
+    lambda[e] = (float)__ddiv_rn(2e-2, dadd((double)norm, 1e-8));
+  }
+  atomicAdd(&deg[v.x], 1);
+  atomicAdd(&deg[v.y], 1);
+}
+
+__global__ void k_scan1(const int* __restrict__ in, int* __restrict__ out, int n) {   // one CTA, exclusive
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int b = min(n, tid * per), e = min(n, b + per);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += in[i];
+  int incl = sum;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = s_warp[tid];
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) w += v; }
+    s_warp[tid] = w;
+  }
+  __syncthreads();
+  int run = incl - sum + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
+  for (int i = b; i < e; ++i) { out[i] = run; run += in[i]; }
+  if (tid == 1023) out[n] = s_warp[31];
+}
+
+__global__ void k_csr_fill(const int2* __restrict__ ev, int nEdges, const int* __restrict__ start, int* __restrict__ fill,
+                           int* __restrict__ keys) {
+  const int e = blockIdx.x * kBlock + threadIdx.x;
+  if (e >= nEdges) return;
+  const int2 v = ev[e];
+  if (v.x < 0) return;
+  keys[start[v.x] + atomicAdd(&fill[v.x], 1)] = 2 * e;       // side 0: "l_v0 -= r"
+  keys[start[v.y] + atomicAdd(&fill[v.y], 1)] = 2 * e + 1;   // side 1: "l_v1 += r"
+}
+
+__global__ void k_csr_sort(const int* __restrict__ start, int nV, int* __restrict__ keys) {
+  const int v = blockIdx.x * kBlock + threadIdx.x;
+  if (v >= nV) return;
+  int* a = keys + start[v];
+  const int n = start[v + 1] - start[v];
+  if (n <= 32) {
+    for (int i = 1; i < n; ++i) {
+      const int x = a[i];
+      int j = i - 1;
+      while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; --j; }
+      a[j + 1] = x;
+    }
+  } else {   // heap sort for hubs
+    for (int st = n / 2 - 1; st >= 0; --st) {
+      int root = st;
+      for (;;) {
+        int ch = 2 * root + 1;
+        if (ch >= n) break;
+        if (ch + 1 < n && a[ch] < a[ch + 1]) ++ch;
+        if (a[root] >= a[ch]) break;
+        const int t = a[root]; a[root] = a[ch]; a[ch] = t; root = ch;
+      }
+    }
+    for (int end = n - 1; end > 0; --end) {
+      const int t0 = a[0]; a[0] = a[end]; a[end] = t0;
+      int root = 0;
+      for (;;) {
+        int ch = 2 * root + 1;
+        if (ch >= end) break;
+        if (ch + 1 < end && a[ch] < a[ch + 1]) ++ch;
+        if (a[root] >= a[ch]) break;
+        const int t = a[root]; a[root] = a[ch]; a[ch] = t; root = ch;
+      }
+    }
+  }
+}
+
+// {Rigid,Graph,Cad}EdgeLoss_forward
+__global__ void k_edges_forward(int kind, const float* __restrict__ V, int nV, const int* __restrict__ F,
+                                const int* __restrict__ E, int nE, int nEdges, const float* __restrict__ rest,
+                                const float* __restrict__ lambda, float* __restrict__ out) {
+  const int e = blockIdx.x * kBlock + threadIdx.x;
+  if (e >= nEdges) return;
+  const int2 v = edge_endpoints(kind, e, F, E, nE);
+  const bool ok = (unsigned)v.x < (unsigned)nV && (unsigned)v.y < (unsigned)nV;
+  const float lam = lambda ? lambda[e] : 1.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float l = 0.f;
+    if (ok) {
+      l = fsub(fsub(__ldg(V + 3 * (size_t)v.y + k), __ldg(V + 3 * (size_t)v.x + k)), rest[3 * (size_t)e + k]);   // rigid_layer.cc:80-82
+      if (lambda) l = fmul(l, lam);                                                                              // cad_layer.cc:117-122
+    }
+    out[3 * (size_t)e + k] = fmul(l, l);
+  }
+}
+
+// one vertex's gradient: contributions in ascending (edge, side) order
+__device__ __forceinline__ void gather_vertex(const float* __restrict__ V, const int2* __restrict__ ev,
+                                              const float* __restrict__ rest, const float* __restrict__ lambda,
+                                              const int* __restrict__ keys, int kb, int ke, float acc[3],
+                                              double* edge_loss) {
+  for (int i = kb; i < ke; ++i) {
+    const int key = keys[i];
+    const int e = key >> 1, side = key & 1;
+    const int2 v = ev[e];
+    float lam2 = 1.f, lam = 1.f;
+    if (lambda) { lam = lambda[e]; lam2 = fmul(lam, lam); }   // cad_layer.cc:186-187
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float r = fsub(fsub(__ldg(V + 3 * (size_t)v.y + k), __ldg(V + 3 * (size_t)v.x + k)), rest[3 * (size_t)e + k]);
+      if (edge_loss && side == 0) { const float l = lambda ? fmul(r, lam) : r; *edge_loss += (double)fmul(l, l); }
+      if (lambda) r = fmul(r, lam2);
+      acc[k] = side ? fadd(acc[k], r) : fsub(acc[k], r);        // rigid_layer.cc:123-128
+    }
+  }
+}
+
+__global__ void k_edges_backward_csr(const float* __restrict__ V, int nV, const int2* __restrict__ ev,
+                                     const float* __restrict__ rest, const float* __restrict__ lambda,
+                                     const int* __restrict__ start, const int* __restrict__ keys, float* __restrict__ grad) {
+  const int v = blockIdx.x * kBlock + threadIdx.x;
+  if (v >= nV) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+  gather_vertex(V, ev, rest, lambda, keys, start[v], start[v + 1], acc, nullptr);
+  grad[3 * (size_t)v] = acc[0]; grad[3 * (size_t)v + 1] = acc[1]; grad[3 * (size_t)v + 2] = acc[2];
+}
+
+// edge-parallel scatter; lanes of a warp that hit the same vertex are summed first
+__global__ void k_edges_backward_atomic(int kind, const float* __restrict__ V, int nV, const int* __restrict__ F,
+                                        const int* __restrict__ E, int nE, int nEdges, const float* __restrict__ rest,
+                                        const float* __restrict__ lambda, float* __restrict__ grad) {
+  const int e = blockIdx.x * kBlock + threadIdx.x;
+  int2 v = make_int2(-1, -1);
+  float r[3] = {0.f, 0.f, 0.f};
+  if (e < nEdges) {
+    v = edge_endpoints(kind, e, F, E, nE);
+    if ((unsigned)v.x < (unsigned)nV && (unsigned)v.y < (unsigned)nV) {
+      float lam2 = 1.f;
+      if (lambda) { const float lam = lambda[e]; lam2 = fmul(lam, lam); }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        r[k] = fsub(fsub(__ldg(V + 3 * (size_t)v.y + k), __ldg(V + 3 * (size_t)v.x + k)), rest[3 * (size_t)e + k]);
+        if (lambda) r[k] = fmul(r[k], lam2);
+      }
+    } else {
+      v = make_int2(-1, -1);
+    }
+  }
+  const cg::coalesced_group active = cg::coalesced_threads();
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int tgt = side ? v.y : v.x;
+    const cg::coalesced_group same = cg::labeled_partition(active, tgt);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float s = cg::reduce(same, side ? r[k] : -r[k], cg::plus<float>());
+      if (tgt >= 0 && same.thread_rank() == 0) atomicAdd(grad + 3 * (size_t)tgt + k, s);
+    }
+  }
+}
+
+// fused per-iteration loss: distance (Jet) + CSR edge gather + masked/weighted sum
+__global__ void __launch_bounds__(kBlock) k_loss_fused(const float* __restrict__ grid, int n, const float* __restrict__ V,
+                                                       int nV, const int2* __restrict__ ev, const float* __restrict__ rest,
+                                                       const float* __restrict__ lambda, const int* __restrict__ start,
+                                                       const int* __restrict__ keys, float w_edge, float mask_thr,
+                                                       double* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ double s_part[kBlock / 32];
+  const int v = blockIdx.x * kBlock + threadIdx.x;
+  double my = 0.0;
+  if (v < nV) {
+    typedef Jet3<float> J;
+    const float x = V[3 * (size_t)v], y = V[3 * (size_t)v + 1], z = V[3 * (size_t)v + 2];
+    J vd = sample<J, float>(grid, n, J(x, 1.f, 0.f, 0.f), J(y, 0.f, 1.f, 0.f), J(z, 0.f, 0.f, 1.f));
+    vd = vd * vd;
+    const float lossD = fmul(vd.a, 0.5f);                                    // rigid_loss_layer.py:11
+    float gD[3] = {(float)((double)vd.v0 * 0.5), (float)((double)vd.v1 * 0.5), (float)((double)vd.v2 * 0.5)};
+    if (mask_thr > 0.f && !(lossD < mask_thr)) gD[0] = gD[1] = gD[2] = 0.f;   // graph_loss_layer.py:18,40
+    float gE[3] = {0.f, 0.f, 0.f};
+    double le = 0.0;
+    if (start) gather_vertex(V, ev, rest, lambda, keys, start[v], start[v + 1], gE, loss ? &le : nullptr);
+    my = (double)lossD + 0.5 * le * (double)w_edge;
+    if (grad) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) grad[3 * (size_t)v + k] = fadd(gD[k], fmul(gE[k], w_edge));   // rigid_loss_layer.py:27
+    }
+  }
+  if (loss) {
+    for (int o = 16; o > 0; o >>= 1) my += __shfl_xor_sync(0xffffffffu, my, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = my;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < kBlock / 32; ++i) t += s_part[i];
+      atomicAdd(loss, t);
+    }
+  }
+}
+
+}  // namespace
+
+void free_edges(Template& T) {
+  cudaFree(T.d_ev); cudaFree(T.d_rest); cudaFree(T.d_lambda); cudaFree(T.d_csr_start); cudaFree(T.d_csr_key);
+  T.d_ev = nullptr; T.d_rest = nullptr; T.d_lambda = nullptr; T.d_csr_start = nullptr; T.d_csr_key = nullptr;
+  T.kind = MO_EDGES_NONE; T.nEdges = 0;
+}
+
+static int edge_count(int kind, int nF, int nE) {
+  return kind == MO_EDGES_RIGID ? 3 * nF : (kind == MO_EDGES_GRAPH ? nE : nE + 3 * nF);
+}
+
+int edges_store(Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
+                cudaStream_t s) {
+  const int nEdges = edge_count(kind, nF, nE);
+  // storage is re-used when the shape is unchanged (every iteration of a re-initialising caller)
+  if (T.kind != kind || T.nEdges != nEdges || T.eV != nV) {
+    MO_CUDA(cudaStreamSynchronize(s));
+    free_edges(T);
+    MO_CUDA(cudaMalloc(&T.d_ev, sizeof(int2) * (size_t)std::max(nEdges, 1)));
+    MO_CUDA(cudaMalloc(&T.d_rest, sizeof(float) * 3 * (size_t)std::max(nEdges, 1)));
+    if (kind == MO_EDGES_CAD) MO_CUDA(cudaMalloc(&T.d_lambda, sizeof(float) * (size_t)std::max(nEdges, 1)));
+    MO_CUDA(cudaMalloc(&T.d_csr_start, sizeof(int) * ((size_t)nV + 1)));
+    MO_CUDA(cudaMalloc(&T.d_csr_key, sizeof(int) * 2 * (size_t)std::max(nEdges, 1)));
+  }
+  T.kind = kind; T.nEdges = nEdges; T.eV = nV; T.eF = nF; T.eE = nE;
+  int* deg = nullptr;   // [nV] degree + [nV] fill cursor
+  MO_CUDA(cudaMallocAsync(&deg, sizeof(int) * 2 * ((size_t)nV + 1), s));
+  MO_CUDA(cudaMemsetAsync(deg, 0, sizeof(int) * 2 * ((size_t)nV + 1), s));
+  if (nEdges > 0) {
+    k_edges_store<<<div_up(nEdges, kBlock), kBlock, 0, s>>>(kind, d_V, nV, d_F, d_E, nE, nEdges, T.d_ev, T.d_rest, T.d_lambda,
+                                                            deg, T.d_stats);
+    MO_LAUNCH_CHECK();
+  }
+  k_scan1<<<1, 1024, 0, s>>>(deg, T.d_csr_start, nV);
+  MO_LAUNCH_CHECK();
+  if (nEdges > 0) {
+    k_csr_fill<<<div_up(nEdges, kBlock), kBlock, 0, s>>>(T.d_ev, nEdges, T.d_csr_start, deg + nV + 1, T.d_csr_key);
+    MO_LAUNCH_CHECK();
+    k_csr_sort<<<div_up(nV, kBlock), kBlock, 0, s>>>(T.d_csr_start, nV, T.d_csr_key);
+    MO_LAUNCH_CHECK();
+  }
+  MO_CUDA(cudaFreeAsync(deg, s));
+  return MO_OK;
+}
+
+int edges_forward(const Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
+                  float* d_out, cudaStream_t s) {
+  const int nEdges = edge_count(kind, nF, nE);
+  if (nEdges == 0) return MO_OK;
+  k_edges_forward<<<div_up(nEdges, kBlock), kBlock, 0, s>>>(kind, d_V, nV, d_F, d_E, nE, nEdges, T.d_rest, T.d_lambda, d_out);
+  MO_LAUNCH_CHECK();
+  return MO_OK;
+}
+
+int edges_backward(const Template& T, const float* d_V, int nV, float* d_grad, cudaStream_t s) {
+  if (nV == 0) return MO_OK;
+  k_edges_backward_csr<<<div_up(nV, kBlock), kBlock, 0, s>>>(d_V, nV, T.d_ev, T.d_rest, T.d_lambda, T.d_csr_start, T.d_csr_key,
+                                                             d_grad);
+  MO_LAUNCH_CHECK();
+  return MO_OK;
+}
+
+int edges_backward_atomic(const Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
+                          int nE, float* d_grad, cudaStream_t s) {
+  const int nEdges = edge_count(kind, nF, nE);
+  MO_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(float) * 3 * (size_t)nV, s));
+  if (nEdges == 0) return MO_OK;
+  k_edges_backward_atomic<<<div_up(nEdges, kBlock), kBlock, 0, s>>>(kind, d_V, nV, d_F, d_E, nE, nEdges, T.d_rest, T.d_lambda,
+                                                                    d_grad);
+  MO_LAUNCH_CHECK();
+  return MO_OK;
+}
+
+int loss_fused(const Template& TD, const Template* TE, const float* d_V, int nV, float w_edge, float mask_thr,
+               double* d_loss, float* d_grad, cudaStream_t s) {
+  if (d_loss) MO_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(double), s));
+  if (nV == 0) return MO_OK;
+  k_loss_fused<<<div_up(nV, kBlock), kBlock, 0, s>>>(TD.d_grid32, TD.N, d_V, nV, TE ? TE->d_ev : nullptr,
+                                                     TE ? TE->d_rest : nullptr, TE ? TE->d_lambda : nullptr,
+                                                     TE ? TE->d_csr_start : nullptr, TE ? TE->d_csr_key : nullptr, w_edge,
+                                                     mask_thr, d_loss, d_grad);
+  MO_LAUNCH_CHECK();
+  return MO_OK;
+}
+
+}  // namespace mo

@@ -1,0 +1,245 @@
+"""Drop-in ``pyDeform`` module: the 18 functions of the reference's pybind11 module
+(src/interface/pydeform.cc:14-39), same names and positional signatures, executed by
+libmeshode_b200.so on the GPU.
+
+Tensors may live on a CUDA device (zero-copy: the kernels read ``data_ptr()`` on torch's
+current stream and results are allocated on the same device) or on the CPU as in the
+reference's scripts (they are staged through the GPU and results come back on the CPU;
+in-place functions write back into the caller's storage).  Unlike the reference, dtype,
+contiguity, shape and ``param_id`` are checked and violations raise.
+
+``import torch`` must precede ``import pyDeform`` as in the reference (README.md:46-50) --
+here simply because this module imports torch itself.
+"""
+import torch
+
+from . import capi
+from .capi import EDGES_CAD, EDGES_GRAPH, EDGES_RIGID, MeshodeError
+from .objio import read_obj, write_obj
+
+__all__ = [
+    "LoadMesh", "LoadCadMesh", "SaveMesh", "InitializeDeformTemplate", "NormalizeByTemplate",
+    "DenormalizeByTemplate", "SolveLinear", "DistanceFieldLoss_forward", "DistanceFieldLoss_backward",
+    "RigidEdgeLoss_forward", "RigidEdgeLoss_backward", "StoreRigidityInformation", "CadEdgeLoss_forward",
+    "CadEdgeLoss_backward", "StoreCadInformation", "GraphEdgeLoss_forward", "GraphEdgeLoss_backward",
+    "StoreGraphInformation",
+]
+
+
+def _device():
+    capi.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dev(t, dtype, cols, name):
+    """Validated device view of ``t`` ([n, cols], ``dtype``, contiguous)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if t.dim() != 2 or t.shape[1] != cols:
+        raise ValueError("%s must have shape [n, %d], got %s" % (name, cols, tuple(t.shape)))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if t.is_cuda:
+        return t
+    return t.to(_device(), non_blocking=False)
+
+
+def _back(res, like):
+    return res if like.is_cuda else res.cpu()
+
+
+def _pid(param_id):
+    if isinstance(param_id, torch.Tensor):
+        param_id = param_id.item()
+    return int(param_id)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() > 0 else 0
+
+
+# ---- mesh I/O (host side, src/interface/mesh_tensor.cc:87-100, :180-186) ---------------
+def LoadMesh(filename):
+    V, F = read_obj(filename)
+    return [torch.from_numpy(V), torch.from_numpy(F)]
+
+
+def SaveMesh(filename, tensorV, tensorF):
+    write_obj(filename, tensorV.detach().cpu().numpy(), tensorF.detach().cpu().numpy())
+
+
+def LoadCadMesh(filename):
+    raise NotImplementedError(
+        "LoadCadMesh needs the CGAL-based subdivision (src/lib/subdivision.cc), which is outside the "
+        "GPU hot path (SURVEY.md s8f); build (V, F, E, V2G, GV, GE) on the host and call the loss layers")
+
+
+def SolveLinear(tensorV, tensorF, tensorE, tensorRef, tensorGraphV, rigidity, with_rot):
+    raise NotImplementedError(
+        "SolveLinear is the sparse direct post-process (src/lib/linear.cc), outside the GPU hot path "
+        "(SURVEY.md s8f)")
+
+
+# ---- template ----------------------------------------------------------------------------
+def InitializeDeformTemplate(tensorV, tensorF, symmetry, grid_resolution):
+    """deform_params.cc:16-40 -> param_id (int)."""
+    V = _dev(tensorV, torch.float32, 3, "tensorV")
+    F = _dev(tensorF, torch.int32, 3, "tensorF").to(V.device)
+    with torch.cuda.device(V.device):
+        return capi.template_create(_ptr(V), V.shape[0], _ptr(F), F.shape[0], int(symmetry), int(grid_resolution),
+                                    _stream(V))
+
+
+def DestroyTemplate(param_id):
+    """Additive: frees the device buffers of a template (the reference never frees g_params)."""
+    capi.template_destroy(_pid(param_id))
+
+
+def _normalize(tensorV, param_id, inverse):
+    V = _dev(tensorV, torch.float32, 3, "tensorV")
+    with torch.cuda.device(V.device):
+        capi.check(capi.lib().mo_normalize_by_template(_ptr(V), V.shape[0], _pid(param_id), inverse, _stream(V)))
+    if V is not tensorV:
+        tensorV.copy_(V)
+
+
+def NormalizeByTemplate(tensorV, param_id):
+    _normalize(tensorV, param_id, 0)
+
+
+def DenormalizeByTemplate(tensorV, param_id):
+    _normalize(tensorV, param_id, 1)
+
+
+# ---- distance field loss -----------------------------------------------------------------
+def DistanceFieldLoss_forward(tensorV, param_id):
+    V = _dev(tensorV, torch.float32, 3, "tensorV")
+    out = torch.empty(V.shape[0], dtype=torch.float32, device=V.device)
+    with torch.cuda.device(V.device):
+        capi.check(capi.lib().mo_distance_forward(_ptr(V), V.shape[0], _pid(param_id), _ptr(out), _stream(V)))
+    return _back(out, tensorV)
+
+
+def DistanceFieldLoss_backward(tensorV, param_id):
+    V = _dev(tensorV, torch.float32, 3, "tensorV")
+    out = torch.empty((V.shape[0], 3), dtype=torch.float32, device=V.device)
+    with torch.cuda.device(V.device):
+        capi.check(capi.lib().mo_distance_backward(_ptr(V), V.shape[0], _pid(param_id), _ptr(out), _stream(V)))
+    return _back(out, tensorV)
+
+
+def DistanceFieldLoss_forward_backward(tensorV, param_id):
+    """Additive: (forward, backward) from one pass over V."""
+    V = _dev(tensorV, torch.float32, 3, "tensorV")
+    out = torch.empty(V.shape[0], dtype=torch.float32, device=V.device)
+    grad = torch.empty((V.shape[0], 3), dtype=torch.float32, device=V.device)
+    with torch.cuda.device(V.device):
+        capi.check(capi.lib().mo_distance_forward_backward(_ptr(V), V.shape[0], _pid(param_id), _ptr(out), _ptr(grad),
+                                                           _stream(V)))
+    return _back(out, tensorV), _back(grad, tensorV)
+
+
+# ---- edge losses -------------------------------------------------------------------------
+def _edges(fn, kind, tensorV, tensorF, tensorE, param_id, out_rows):
+    V = _dev(tensorV, torch.float32, 3, "tensorV")
+    F = _dev(tensorF, torch.int32, 3, "tensorF").to(V.device) if tensorF is not None else None
+    E = _dev(tensorE, torch.int32, 2, "tensorE").to(V.device) if tensorE is not None else None
+    nF = F.shape[0] if F is not None else 0
+    nE = E.shape[0] if E is not None else 0
+    out = None
+    args = [_pid(param_id), kind, _ptr(V), V.shape[0], _ptr(F), nF, _ptr(E), nE]
+    if out_rows is not None:
+        rows = {"edges": {EDGES_RIGID: 3 * nF, EDGES_GRAPH: nE, EDGES_CAD: nE + 3 * nF}[kind], "verts": V.shape[0]}[out_rows]
+        out = torch.empty((rows, 3), dtype=torch.float32, device=V.device)
+        args.append(_ptr(out))
+    with torch.cuda.device(V.device):
+        capi.check(fn(*args, _stream(V)))
+    return _back(out, tensorV) if out is not None else None
+
+
+def StoreRigidityInformation(tensorV, tensorF, param_id):
+    _edges(capi.lib().mo_edges_store, EDGES_RIGID, tensorV, tensorF, None, param_id, None)
+
+
+def RigidEdgeLoss_forward(tensorV, tensorF, param_id):
+    return _edges(capi.lib().mo_edges_forward, EDGES_RIGID, tensorV, tensorF, None, param_id, "edges")
+
+
+def RigidEdgeLoss_backward(tensorV, tensorF, param_id):
+    return _edges(capi.lib().mo_edges_backward, EDGES_RIGID, tensorV, tensorF, None, param_id, "verts")
+
+
+def StoreGraphInformation(tensorV, tensorE, param_id):
+    _edges(capi.lib().mo_edges_store, EDGES_GRAPH, tensorV, None, tensorE, param_id, None)
+
+
+def GraphEdgeLoss_forward(tensorV, tensorE, param_id):
+    return _edges(capi.lib().mo_edges_forward, EDGES_GRAPH, tensorV, None, tensorE, param_id, "edges")
+
+
+def GraphEdgeLoss_backward(tensorV, tensorE, param_id):
+    return _edges(capi.lib().mo_edges_backward, EDGES_GRAPH, tensorV, None, tensorE, param_id, "verts")
+
+
+def StoreCadInformation(tensorV, tensorF, tensorE, param_id):
+    _edges(capi.lib().mo_edges_store, EDGES_CAD, tensorV, tensorF, tensorE, param_id, None)
+
+
+def CadEdgeLoss_forward(tensorV, tensorF, tensorE, param_id):
+    return _edges(capi.lib().mo_edges_forward, EDGES_CAD, tensorV, tensorF, tensorE, param_id, "edges")
+
+
+def CadEdgeLoss_backward(tensorV, tensorF, tensorE, param_id):
+    return _edges(capi.lib().mo_edges_backward, EDGES_CAD, tensorV, tensorF, tensorE, param_id, "verts")
+
+
+# ---- additive helpers used by the device-native layers and the tests ------------------------
+def EdgeLoss_backward_atomic(kind, tensorV, tensorF, tensorE, param_id):
+    return _edges(capi.lib().mo_edges_backward_atomic, kind, tensorV, tensorF, tensorE, param_id, "verts")
+
+
+def LossForwardBackward(tensorV, dist_param_id, edge_param_id, w_edge=1.0, mask_threshold=0.0, want_loss=True,
+                        want_grad=True):
+    """One launch: loss (0-d float64 tensor) and gradient [n,3] of the layers' combined loss."""
+    V = _dev(tensorV, torch.float32, 3, "tensorV")
+    loss = torch.empty((), dtype=torch.float64, device=V.device) if want_loss else None
+    grad = torch.empty((V.shape[0], 3), dtype=torch.float32, device=V.device) if want_grad else None
+    with torch.cuda.device(V.device):
+        capi.check(capi.lib().mo_loss_forward_backward(_pid(dist_param_id), _pid(edge_param_id), _ptr(V), V.shape[0],
+                                                       float(w_edge), float(mask_threshold),
+                                                       loss.data_ptr() if want_loss else 0, _ptr(grad), _stream(V)))
+    return (_back(loss, tensorV) if want_loss else None), (_back(grad, tensorV) if want_grad else None)
+
+
+def GetTemplateInfo(param_id):
+    return capi.template_info(_pid(param_id), torch.cuda.current_stream().cuda_stream)
+
+
+def GetGrid(param_id, z0=0, z1=None):
+    """Additive (tests / z-slab all-gather): (grid_f64 [N,N,N], grid_f32, nearest) torch tensors
+    holding slices [z0,z1) of the template's fields (other slices zero)."""
+    pid = _pid(param_id)
+    N = capi.template_info(pid, torch.cuda.current_stream().cuda_stream)["N"]
+    z1 = N if z1 is None else z1
+    dev = _device()
+    g64 = torch.zeros((N, N, N), dtype=torch.float64, device=dev)
+    g32 = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
+    idx = torch.zeros((N, N, N), dtype=torch.int32, device=dev)
+    capi.check(capi.lib().mo_template_copy_grid(pid, 0, z0, z1, g64.data_ptr(), g32.data_ptr(), idx.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+    return g64, g32, idx
+
+
+def SetGrid(param_id, g64, g32, idx, z0=0, z1=None):
+    """Additive: writes slices [z0,z1) of full-size device tensors into the template (after an all-gather)."""
+    pid = _pid(param_id)
+    N = g32.shape[0]
+    z1 = N if z1 is None else z1
+    capi.check(capi.lib().mo_template_copy_grid(pid, 1, z0, z1, _ptr(g64), _ptr(g32), _ptr(idx),
+                                                torch.cuda.current_stream().cuda_stream))

@@ -1,0 +1,6 @@
+"""`import pyDeform` drop-in (reference: src/interface/pydeform.cc). Re-exports meshode_b200.pyDeform."""
+import torch  # noqa: F401  (the reference requires torch to be imported first; README.md:46-50)
+
+from meshode_b200.pyDeform import *  # noqa: F401,F403
+from meshode_b200.pyDeform import (DestroyTemplate, DistanceFieldLoss_forward_backward, EdgeLoss_backward_atomic,  # noqa: F401
+                                   GetGrid, GetTemplateInfo, LossForwardBackward, SetGrid)
