@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- deformation pairs/sec (BASELINE.json metric) on N B200s of one node, plus the
+128^3 distance-field build.
+
+A *step* is one pass of the hot path over this rank's batch of synthetic shape pairs (cfg4 of
+BASELINE.json: grid 64, 5 000-vertex meshes, rigid loss, Adam lr 1e-3 x 10 000 iterations):
+for every pair InitializeDeformTemplate (normalise + distance field), NormalizeByTemplate,
+StoreRigidityInformation, the fused Adam loop, DenormalizeByTemplate.  Pairs are independent, so
+ranks shard them with no data-path collective (weak scaling: every rank owns --pairs pairs).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the CPU restatement of the reference (oracle/, kind "port": the reference
+itself cannot be compiled here) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "deformation pairs/sec"
+UNIT = "pairs/s"
+# algorithmic HBM bytes of one Adam iteration of one pair (28 B/vertex fused
+# trilinear fwd+bwd, 20 B/edge fused edge fwd+bwd, 72 B/vertex Adam state + parameter traffic)
+def pair_iter_bytes(nV, nE):
+    return 28 * nV + 20 * nE + 72 * nV
+
+
+FLOP_PER_TEST = 74  # canonical Ericson face-region path
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=3625, help="pairs per rank and step (cfg4: 3625)")
+    ap.add_argument("--verts", type=int, default=5000)
+    ap.add_argument("--grid", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=10000)
+    ap.add_argument("--no-sdf128", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of wall clock for the CPU baseline sample")
+    return ap.parse_args()
+
+
+def config_of(a):
+    return {"workload": "cfg4: %d synthetic shape pairs per GPU, %d-vertex source / %d-triangle target, grid %d^3, "
+                        "rigid loss, Adam lr 1e-3 x %d iterations" % (a.pairs, a.verts, 2 * a.verts - 4, a.grid, a.iters),
+            "pairs_per_gpu": a.pairs, "verts": a.verts, "grid": a.grid, "adam_iters": a.iters,
+            "l2": "inputs (%.2f GB per step) exceed the 126 MB L2; no explicit flush" %
+                  (a.pairs * (a.verts * 12 * 2 + (2 * a.verts - 4) * 12 * 2) / 1e9)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(a, budget_s, pairs_offset=0):
+    """Runs one pair per host core (grid build + a slice of the Adam loop), returns
+    (pairs_per_second_full_work, description).  The Adam part is linear in the iteration count and
+    is scaled to the full count; the build part is measured in full."""
+    from meshode_b200.synth import synth_pair
+    from oracle import oracle as O
+
+    O.lib()
+    cores = os.cpu_count() or 1
+    pairs = [synth_pair(pairs_offset + i, a.verts, a.verts) for i in range(cores)]
+    # size the Adam slice from a short probe on one core
+    srcV, srcF, tarV, tarF = pairs[0]
+    t0 = time.perf_counter()
+    tm = O.Template(tarV, tarF, a.grid, threads=1)
+    t_build = time.perf_counter() - t0
+    src_n = O.normalize_by_template(srcV, tm.scale, tm.trans)
+    rest = O.store_rigid(src_n, srcF)
+    t0 = time.perf_counter()
+    O.rigid_adam(tm.grid, src_n, srcF, rest, 50, 1e-3)
+    t_it = (time.perf_counter() - t0) / 50
+    it_sample = int(max(50, min(a.iters, (budget_s - t_build) / max(t_it, 1e-9))))
+    times = [None] * cores
+
+    def work(i):
+        sV, sF, tV, tF = pairs[i]
+        t0 = time.perf_counter()
+        T = O.Template(tV, tF, a.grid, threads=1)
+        sn = O.normalize_by_template(sV, T.scale, T.trans)
+        r = O.store_rigid(sn, sF)
+        t1 = time.perf_counter()
+        V, _ = O.rigid_adam(T.grid, sn, sF, r, it_sample, 1e-3)
+        O.denormalize_by_template(V, T.scale, T.trans)
+        t2 = time.perf_counter()
+        times[i] = (t1 - t0, t2 - t1)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    wall = time.perf_counter() - t0
+    build = float(np.mean([x[0] for x in times]))
+    adam = float(np.mean([x[1] for x in times])) * (a.iters / it_sample)
+    per_pair_core = build + adam
+    value = cores / per_pair_core
+    desc = ("%d pairs, one per host thread (ctypes releases the GIL): full grid-%d build (%.2f s) + %d of %d Adam "
+            "iterations (scaled x%.2f -> %.2f s) per pair; wall %.1f s" %
+            (cores, a.grid, build, it_sample, a.iters, a.iters / it_sample, adam, wall))
+    return value, desc, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_steps = a.warmup + a.steps
+    budget = max(4.0, min(a.cpu_budget, 150.0 / max(n_steps, 1)))
+    vals, desc, cores = [], "", 1
+    for s in range(n_steps):
+        v, desc, cores = cpu_sample(a, budget, pairs_offset=0)
+        if s >= a.warmup:
+            vals.append(v)
+    value = float(np.mean(vals)) if vals else float("nan")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * (os.cpu_count() or 1) / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(a),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            hi = [x for x in sm if x >= 0.5 * max(sm)]   # samples under load
+            out = {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    from meshode_b200 import capi, engine
+    from meshode_b200 import pyDeform as pd
+    from meshode_b200.synth import synth_mesh, synth_pair
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    capi.require_device()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic inputs: pinned host copies and resident device copies ------------------------
+    n = a.pairs
+    first = rank * n
+    host_pairs = []
+    for i in range(n):
+        arrs = synth_pair(first + i, a.verts, a.verts)
+        host_pairs.append(tuple(torch.from_numpy(x).pin_memory() for x in arrs))
+    dev_pairs = [tuple(t.to(dev) for t in p) for p in host_pairs]
+    nV = a.verts
+    nE = 3 * host_pairs[0][1].shape[0]
+    h2d = sum(t.numel() * t.element_size() for p in host_pairs for t in p)
+    d2h = sum(p[0].numel() * 4 for p in host_pairs)
+    host_out = [torch.empty_like(p[0]).pin_memory() for p in host_pairs]
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    deform_ms = []
+
+    def step(pairs, e2e=False):
+        batch = engine.PairBatch(pairs, grid_resolution=a.grid, device=dev)
+        e0, e1 = ev(), ev()
+        e0.record()
+        batch.deform(iters=a.iters, lr=1e-3)
+        e1.record()
+        out = batch.finalize()
+        if e2e:
+            for o, h in zip(out, host_out):
+                h.copy_(o, non_blocking=True)
+        batch.release()
+        return e0, e1
+
+    # ---- warm-up ----------------------------------------------------------------------------------
+    for _ in range(a.warmup):
+        step(dev_pairs)
+    barrier()
+
+    # ---- timed: inputs resident in HBM --------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = capi.lib().mo_launch_count()
+    t_start, t_end = ev(), ev()
+    barrier()
+    t_start.record()
+    evs = [step(dev_pairs) for _ in range(a.steps)]
+    t_end.record()
+    barrier()
+    launches = capi.lib().mo_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    deform_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+
+    # ---- timed: end to end from pinned host buffers ----------------------------------------------------
+    step(host_pairs, e2e=True)
+    barrier()
+    t_start2, t_end2 = ev(), ev()
+    n_e2e = max(1, min(a.steps, 2))
+    t_start2.record()
+    for _ in range(n_e2e):
+        step(host_pairs, e2e=True)
+    t_end2.record()
+    barrier()
+    ms_e2e = t_start2.elapsed_time(t_end2) / n_e2e
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = t.tolist()
+    ms_step = ms_total / a.steps
+    value = world * n / (ms_step * 1e-3)
+    e2e_value = world * n / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        d_ms = float(np.mean(deform_ms))
+        alg = pair_iter_bytes(nV, nE) * a.iters * n
+        ach = alg / (d_ms * 1e-3) / 1e9
+        roof = {"kernel": "k_deform_adam (one launch per step and rank: %d pairs x %d iterations)" % (n, a.iters),
+                "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "peak_source": hbm_src + " (sustained: timed inside a seconds-long step)",
+                "launch_ms": d_ms, "share_of_step": d_ms / ms_step,
+                "note": "algorithmic bytes = (28*V + 20*E + 72*V) per pair-iteration (SURVEY s8d) = %.3f MB; the kernel "
+                        "keeps V, rest positions, gradient and Adam moments on chip, so HBM is not its limiter and the "
+                        "fraction can exceed 1" % (pair_iter_bytes(nV, nE) / 1e6)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_of(a), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": int(launches), "roofline": roof}
+
+    # ---- secondary metric: 128^3 distance-field build on a 50 000-triangle target (cfg3) -------------------
+    if rank == 0 and not a.no_sdf128:
+        V, F = synth_mesh(25002, 1)
+        tV, tF = torch.from_numpy(V).to(dev), torch.from_numpy(F).to(dev)
+        sink = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
+        s = torch.cuda.current_stream().cuda_stream
+        # FP32 denominator: FFMA chain, 8 CTAs of 256 threads per SM
+        it_f = 20000
+        for _ in range(2):
+            capi.check(capi.lib().mo_microbench_fp32(148 * 8, 256, it_f, sink.data_ptr(), s))
+        f0, f1 = ev(), ev()
+        f0.record()
+        capi.check(capi.lib().mo_microbench_fp32(148 * 8, 256, it_f, sink.data_ptr(), s))
+        f1.record()
+        torch.cuda.synchronize()
+        fp32_tf = 148 * 8 * 256 * it_f * 8 * 2 / (f0.elapsed_time(f1) * 1e-3) / 1e12
+        times, stats = [], None
+        for k in range(3 + 5):
+            b0, b1 = ev(), ev()
+            b0.record()
+            pid = pd.InitializeDeformTemplate(tV, tF, 0, 128)
+            b1.record()
+            torch.cuda.synchronize()
+            if k >= 3:
+                times.append(b0.elapsed_time(b1))
+            stats = capi.template_build_stats(pid)
+            pd.DestroyTemplate(pid)
+        ms = float(np.mean(times))
+        tests = stats["fp32_tests"] + stats["cull_tests"]
+        tf = tests * FLOP_PER_TEST / (ms * 1e-3) / 1e12
+        line["sdf_build_128"] = {
+            "metric": "grid-SDF build ms at 128^3", "value": ms, "unit": "ms", "target_triangles": int(F.shape[0]),
+            "fp32_tests": stats["fp32_tests"], "cull_tests": stats["cull_tests"], "fp64_tests": stats["fp64_tests"],
+            "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": tf / fp32_tf,
+                         "traffic": None,
+                         "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 "
+                                        "entry); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                         "note": "achieved = (dense + cull point-triangle tests executed, counted by the kernel) x 74 FLOP "
+                                 "/ build time including binning; brute-force-equivalent N^3*M*74 = %.3g FLOP" %
+                                 (128 ** 3 * F.shape[0] * 74.0)}}
+        line["fp32_tflops_measured"] = fp32_tf
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------
+    if rank == 0 and world == 1 and not a.no_cpu:
+        v, desc, cores = cpu_sample(a, a.cpu_budget)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_b200(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,6 +36,12 @@ enum { MO_EDGES_NONE = -1, MO_EDGES_RIGID = 0, MO_EDGES_GRAPH = 1, MO_EDGES_CAD 
 
 int mo_version(void);
 const char* mo_last_error(void);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches). */
+unsigned long long mo_launch_count(void);
+/* FFMA-chain microbenchmark used as the FP32 roofline denominator: every thread runs `iters`
+ * dependent-free FMA groups (8 independent chains); flops = blocks*threads*iters*8*2.
+ * d_sink (>= blocks*threads floats) keeps the result alive. */
+int mo_microbench_fp32(int blocks, int threads, int iters, float* d_sink, mo_stream_t stream);
 /* number of visible CUDA devices (0 when there is none). */
 int mo_device_count(void);
 
@@ -147,6 +153,25 @@ int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, c
  * (sum accumulated in FP64); d_grad float32 [nV,3]. Either may be NULL. */
 int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* d_V, int nV, float w_edge,
                              float mask_threshold, double* d_loss, float* d_grad, mo_stream_t stream);
+
+/* ---- whole optimisation loops (src/python/rigid_deform.py:32-41) ----------------------- */
+/* For each of B independent pairs: `iters` iterations of
+ *     grad = DistanceFieldLoss_backward(V, dist_pid) + {Rigid,Graph}EdgeLoss_backward(V, edge_pid)
+ *     torch.optim.Adam step (lr, betas, eps; float32 state, bias correction as in
+ *     torch/optim/adam.py::_single_tensor_adam)
+ * in ONE persistent kernel, one CTA per pair, V / rest positions / gradient resident in shared
+ * memory.  h_dist_pids / h_edge_pids are HOST arrays of B param_ids (they may be equal, as in
+ * rigid_loss_layer.py, or differ, as in graph_loss2_layer.py:18-19); h_dV is a HOST array of B
+ * device pointers to normalised float32 [nV_i,3] vertices, updated in place.  Edges (RIGID or
+ * GRAPH) must have been stored with mo_edges_store for nV_i <= 6144 vertices.  Bit-identical
+ * to running the per-call entry points and Adam in float32 on the CPU. */
+int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* const* h_dV, int B, int iters,
+                         double lr, double beta1, double beta2, double eps, mo_stream_t stream);
+/* Same loop for one pair of any size (state in HBM/L2, two launches per iteration), with the
+ * graph layer's options: edge weight (rigidity^2) and distance-gradient mask threshold
+ * (graph_loss_layer.py:18,40-42; mask_threshold <= 0 disables the mask). */
+int mo_deform_adam_large(int dist_pid, int edge_pid, float* d_V, int nV, float w_edge, float mask_threshold,
+                         int iters, double lr, double beta1, double beta2, double eps, mo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmeshode_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
-SOURCES = ["sdf_build.cu", "sampler.cu", "edges.cu", "capi.cu", "deform.cu", "ceres_path.cu"]
+SOURCES = ["sdf_build.cu", "sampler.cu", "edges.cu", "capi.cu", "deform.cu", "microbench.cu", "ceres_path.cu"]
 
 
 def _nvcc():
@@ -46,7 +46,7 @@ def build_lib(force=False, verbose=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _newer(LIB, objs):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([nvcc] + NVCC_FLAGS[:2] + ["-shared", "-o", LIB] + objs)
     return LIB
 
 

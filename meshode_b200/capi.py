@@ -21,6 +21,8 @@ SIGNATURES = {
     "mo_version": [],
     "mo_last_error": [],
     "mo_device_count": [],
+    "mo_launch_count": [],
+    "mo_microbench_fp32": [_i, _i, _i, _vp, _vp],
     "mo_template_create": [_vp, _i, _vp, _i, _i, _i, _vp, _ip],
     "mo_template_create_slab": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _ip],
     "mo_template_create_normalized": [_vp, _i, _vp, _i, _i, _d, _dp, _vp, _ip],
@@ -40,13 +42,10 @@ SIGNATURES = {
     "mo_edges_backward": [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp],
     "mo_edges_backward_atomic": [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp],
     "mo_loss_forward_backward": [_i, _i, _vp, _i, _f, _f, _vp, _vp, _vp],
-    "mo_rot_edges_cost_grad": [_vp, _vp, _i, _vp, _i, _vp, _d, _vp, _vp, _vp, _vp],
-    "mo_deform_cost_grad": [_i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _vp],
-    "mo_deform_rigid_adam": [_i, _vp, _i, _vp, _i, _i, _d, _vp, _vp],
-    "mo_deform_batch_adam": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp],
-    "mo_template_create_batch": [_vp, _i, _vp, _i, _i, _i, _vp, _ip],
+    "mo_deform_batch_adam": [_ip, _ip, C.POINTER(_vp), _i, _i, _d, _d, _d, _d, _vp],
+    "mo_deform_adam_large": [_i, _i, _vp, _i, _f, _f, _i, _d, _d, _d, _d, _vp],
 }
-_RESTYPES = {"mo_last_error": C.c_char_p}
+_RESTYPES = {"mo_last_error": C.c_char_p, "mo_launch_count": C.c_ulonglong}
 
 _lib = None
 

@@ -9,6 +9,7 @@
 
 namespace mo {
 
+std::atomic<unsigned long long> g_launches{0};
 static thread_local std::string t_error;
 void set_error(const std::string& s) { t_error = s; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
@@ -17,6 +18,25 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   t_error = buf;
   cudaGetLastError();   // clear the sticky flag of non-fatal errors
   return MO_ERR_CUDA;
+}
+
+cudaError_t dev_alloc_bytes(void** p, size_t bytes, cudaStream_t s) {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::call_once(once[dev & 63], [dev]() {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+  });
+  return cudaMallocAsync(p, bytes ? bytes : 1, s);
+}
+void dev_free(void* p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
 }
 
 namespace {
@@ -33,22 +53,22 @@ Template* lookup(int pid) {
   return g_templates[pid].get();
 }
 
-void release(Template& T) {
-  free_edges(T);
-  cudaFree(T.d_Vn); cudaFree(T.d_F); cudaFree(T.d_grid64); cudaFree(T.d_grid32); cudaFree(T.d_nearest);
-  cudaFree(T.d_xf); cudaFree(T.d_stats);
+void release(Template& T, cudaStream_t s = 0) {
+  free_edges(T, s);
+  dev_free(T.d_Vn, s); dev_free(T.d_F, s); dev_free(T.d_grid64, s); dev_free(T.d_grid32, s); dev_free(T.d_nearest, s);
+  dev_free(T.d_xf, s); dev_free(T.d_stats, s);
 }
 
-int allocate(Template& T) {
+int allocate(Template& T, cudaStream_t s) {
   const size_t nvox = (size_t)T.N * T.N * T.N;
   MO_CUDA(cudaGetDevice(&T.device));
-  MO_CUDA(cudaMalloc(&T.d_Vn, sizeof(double) * 3 * (size_t)T.nV));
-  MO_CUDA(cudaMalloc(&T.d_F, sizeof(int) * 3 * (size_t)T.nF));
-  MO_CUDA(cudaMalloc(&T.d_grid64, sizeof(double) * nvox));
-  MO_CUDA(cudaMalloc(&T.d_grid32, sizeof(float) * nvox));
-  MO_CUDA(cudaMalloc(&T.d_nearest, sizeof(int) * nvox));
-  MO_CUDA(cudaMalloc(&T.d_xf, sizeof(double) * 4));
-  MO_CUDA(cudaMalloc(&T.d_stats, sizeof(unsigned long long) * 4));
+  MO_CUDA(dev_alloc(&T.d_Vn, 3 * (size_t)T.nV, s));
+  MO_CUDA(dev_alloc(&T.d_F, 3 * (size_t)T.nF, s));
+  MO_CUDA(dev_alloc(&T.d_grid64, nvox, s));
+  MO_CUDA(dev_alloc(&T.d_grid32, nvox, s));
+  MO_CUDA(dev_alloc(&T.d_nearest, nvox, s));
+  MO_CUDA(dev_alloc(&T.d_xf, 4, s));
+  MO_CUDA(dev_alloc(&T.d_stats, 4, s));
   return MO_OK;
 }
 
@@ -68,8 +88,8 @@ int create_common(const float* d_V, const double* d_Vn, int nV, const int* d_F, 
   MO_REQUIRE(0 <= z0 && z0 < z1 && z1 <= N, "bad z-slab");
   std::unique_ptr<Template> T(new Template());
   T->N = N; T->nV = nV; T->nF = nF; T->z0 = z0; T->z1 = z1;
-  int rc = allocate(*T);
-  if (rc != MO_OK) { release(*T); return rc; }
+  int rc = allocate(*T, s);
+  if (rc != MO_OK) { release(*T, s); return rc; }
   cudaError_t e = cudaMemcpyAsync(T->d_F, d_F, sizeof(int) * 3 * (size_t)nF, cudaMemcpyDeviceToDevice, s);
   if (e == cudaSuccess && d_Vn) {
     e = cudaMemcpyAsync(T->d_Vn, d_Vn, sizeof(double) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, s);
@@ -77,9 +97,9 @@ int create_common(const float* d_V, const double* d_Vn, int nV, const int* d_F, 
     if (e == cudaSuccess) e = cudaMemcpyAsync(T->d_xf, xf, sizeof(xf), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // xf lives on this frame
   }
-  if (e != cudaSuccess) { release(*T); return cuda_fail(e, "template upload", __FILE__, __LINE__); }
+  if (e != cudaSuccess) { release(*T, s); return cuda_fail(e, "template upload", __FILE__, __LINE__); }
   rc = d_Vn ? build_field_from_normalized(*T, s) : build_field_from_f32(*T, d_V, s);
-  if (rc != MO_OK) { release(*T); return rc; }
+  if (rc != MO_OK) { release(*T, s); return rc; }
   return publish(T, out);
 }
 
@@ -102,6 +122,7 @@ using namespace mo;
 extern "C" {
 
 int mo_version(void) { return 1; }
+unsigned long long mo_launch_count(void) { return g_launches.load(); }
 const char* mo_last_error(void) { return t_error.c_str(); }
 int mo_device_count(void) {
   int n = 0;
@@ -135,8 +156,8 @@ int mo_template_destroy(int param_id) {
     }
     T = std::move(g_templates[param_id]);
   }
-  cudaDeviceSynchronize();
-  release(*T);
+  // returned to the pool in the order of the legacy default stream (which joins all blocking streams)
+  release(*T, 0);
   return MO_OK;
 }
 
@@ -327,6 +348,30 @@ int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* 
   return loss_fused(*TD, TE, d_V, nV, w_edge, mask_threshold, d_loss, d_grad, (cudaStream_t)stream);
 }
 
+
+int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* const* h_dV, int B, int iters, double lr,
+                         double beta1, double beta2, double eps, mo_stream_t stream) {
+  MO_REQUIRE(B >= 0 && iters >= 0, "negative count");
+  MO_REQUIRE(B == 0 || (h_dist_pids && h_edge_pids && h_dV), "null pointer");
+  std::vector<Template*> td(B), te(B);
+  for (int i = 0; i < B; ++i) {
+    td[i] = lookup(h_dist_pids[i]);
+    te[i] = lookup(h_edge_pids[i]);
+    if (!td[i] || !te[i]) return MO_ERR_BAD_HANDLE;
+    MO_REQUIRE(h_dV[i] != nullptr, "null vertex pointer");
+  }
+  return deform_batch_adam(td.data(), te.data(), h_dV, B, iters, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+int mo_deform_adam_large(int dist_pid, int edge_pid, float* d_V, int nV, float w_edge, float mask_threshold, int iters,
+                         double lr, double beta1, double beta2, double eps, mo_stream_t stream) {
+  Template* TD = lookup(dist_pid);
+  Template* TE = lookup(edge_pid);
+  if (!TD || !TE) return MO_ERR_BAD_HANDLE;
+  if (TE->kind == MO_EDGES_NONE) { set_error("no edges stored for edge_pid"); return MO_ERR_STATE; }
+  MO_REQUIRE(nV == TE->eV && (nV == 0 || d_V) && iters >= 0, "vertex count differs from the stored one / null pointer");
+  return deform_adam_large(*TD, *TE, d_V, nV, w_edge, mask_threshold, iters, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
 
 int mo_normalize_by_template(float* d_V, int n, int param_id, int inverse, mo_stream_t stream) {
   Template* T = lookup(param_id);

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <string>
 
@@ -31,7 +32,19 @@ struct Template {
   float* d_lambda = nullptr;    // [nEdges] (CAD only)
   int* d_csr_start = nullptr;   // [eV+1]
   int* d_csr_key = nullptr;     // [2*nEdges] 2*edge + side, ascending per vertex
+  float* d_v0 = nullptr;        // [eV,3] vertices at store time (rest = V0[v1] - V0[v0])
+  unsigned short* d_ell = nullptr;   // [ell_D][eV] other endpoint per incident edge, built on first deform
+  int ell_D = 0;
 };
+
+// Stream-ordered allocation from the device's default memory pool (release threshold raised so
+// that per-pair templates are recycled without driver calls).  dev_free returns the block to the
+// pool in the order of the legacy default stream.
+cudaError_t dev_alloc_bytes(void** p, size_t bytes, cudaStream_t s);
+template <class T> inline cudaError_t dev_alloc(T** p, size_t count, cudaStream_t s) {
+  return dev_alloc_bytes(reinterpret_cast<void**>(p), count * sizeof(T), s);
+}
+void dev_free(void* p, cudaStream_t s = 0);
 
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -41,7 +54,14 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     cudaError_t e__ = (call);                                                \
     if (e__ != cudaSuccess) return ::mo::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
-#define MO_LAUNCH_CHECK() MO_CUDA(cudaGetLastError())
+// every kernel launch of this library is followed by MO_LAUNCH_CHECK, which also counts it
+// (mo_launch_count: the "gpu_launches" figure of bench.py)
+extern std::atomic<unsigned long long> g_launches;
+#define MO_LAUNCH_CHECK()                                             \
+  do {                                                                \
+    ::mo::g_launches.fetch_add(1, std::memory_order_relaxed);         \
+    MO_CUDA(cudaGetLastError());                                      \
+  } while (0)
 #define MO_REQUIRE(cond, msg)                                                \
   do {                                                                       \
     if (!(cond)) { ::mo::set_error(std::string("bad argument: ") + msg); return MO_ERR_BAD_ARG; } \
@@ -54,7 +74,7 @@ int build_field_from_normalized(Template& T, cudaStream_t s);
 int launch_distance_f32(const Template& T, const float* d_V, int n, float* d_out, float* d_grad, int mode, cudaStream_t s);
 int launch_distance_f64(const Template& T, const double* d_P, int n, double* d_val, double* d_grad, cudaStream_t s);
 // edges.cu
-void free_edges(Template& T);
+void free_edges(Template& T, cudaStream_t s = 0);
 int edges_store(Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
                 cudaStream_t s);
 int edges_forward(const Template& T, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
@@ -64,6 +84,12 @@ int edges_backward_atomic(const Template& T, int kind, const float* d_V, int nV,
                           int nE, float* d_grad, cudaStream_t s);
 int loss_fused(const Template& TD, const Template* TE, const float* d_V, int nV, float w_edge, float mask_thr,
                double* d_loss, float* d_grad, cudaStream_t s);
+
+// deform.cu
+int deform_batch_adam(Template* const* TD, Template* const* TE, float* const* h_V, int B, int iters, double lr,
+                      double beta1, double beta2, double eps, cudaStream_t s);
+int deform_adam_large(Template& TD, Template& TE, float* d_V, int nV, float w_edge, float mask_thr, int iters, double lr,
+                      double beta1, double beta2, double eps, cudaStream_t s);
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -253,9 +253,11 @@ __global__ void __launch_bounds__(kBlock) k_loss_fused(const float* __restrict__
 
 }  // namespace
 
-void free_edges(Template& T) {
-  cudaFree(T.d_ev); cudaFree(T.d_rest); cudaFree(T.d_lambda); cudaFree(T.d_csr_start); cudaFree(T.d_csr_key);
+void free_edges(Template& T, cudaStream_t s) {
+  dev_free(T.d_ev, s); dev_free(T.d_rest, s); dev_free(T.d_lambda, s); dev_free(T.d_csr_start, s); dev_free(T.d_csr_key, s);
+  dev_free(T.d_v0, s); dev_free(T.d_ell, s);
   T.d_ev = nullptr; T.d_rest = nullptr; T.d_lambda = nullptr; T.d_csr_start = nullptr; T.d_csr_key = nullptr;
+  T.d_v0 = nullptr; T.d_ell = nullptr; T.ell_D = 0;
   T.kind = MO_EDGES_NONE; T.nEdges = 0;
 }
 
@@ -268,14 +270,16 @@ int edges_store(Template& T, int kind, const float* d_V, int nV, const int* d_F,
   const int nEdges = edge_count(kind, nF, nE);
   // storage is re-used when the shape is unchanged (every iteration of a re-initialising caller)
   if (T.kind != kind || T.nEdges != nEdges || T.eV != nV) {
-    MO_CUDA(cudaStreamSynchronize(s));
-    free_edges(T);
-    MO_CUDA(cudaMalloc(&T.d_ev, sizeof(int2) * (size_t)std::max(nEdges, 1)));
-    MO_CUDA(cudaMalloc(&T.d_rest, sizeof(float) * 3 * (size_t)std::max(nEdges, 1)));
-    if (kind == MO_EDGES_CAD) MO_CUDA(cudaMalloc(&T.d_lambda, sizeof(float) * (size_t)std::max(nEdges, 1)));
-    MO_CUDA(cudaMalloc(&T.d_csr_start, sizeof(int) * ((size_t)nV + 1)));
-    MO_CUDA(cudaMalloc(&T.d_csr_key, sizeof(int) * 2 * (size_t)std::max(nEdges, 1)));
+    free_edges(T, s);
+    MO_CUDA(dev_alloc(&T.d_ev, (size_t)std::max(nEdges, 1), s));
+    MO_CUDA(dev_alloc(&T.d_rest, 3 * (size_t)std::max(nEdges, 1), s));
+    if (kind == MO_EDGES_CAD) MO_CUDA(dev_alloc(&T.d_lambda, (size_t)std::max(nEdges, 1), s));
+    MO_CUDA(dev_alloc(&T.d_csr_start, (size_t)nV + 1, s));
+    MO_CUDA(dev_alloc(&T.d_csr_key, 2 * (size_t)std::max(nEdges, 1), s));
+    MO_CUDA(dev_alloc(&T.d_v0, 3 * (size_t)std::max(nV, 1), s));
   }
+  if (T.d_ell) { dev_free(T.d_ell, s); T.d_ell = nullptr; T.ell_D = 0; }
+  if (nV > 0) MO_CUDA(cudaMemcpyAsync(T.d_v0, d_V, sizeof(float) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, s));
   T.kind = kind; T.nEdges = nEdges; T.eV = nV; T.eF = nF; T.eE = nE;
   int* deg = nullptr;   // [nV] degree + [nV] fill cursor
   MO_CUDA(cudaMallocAsync(&deg, sizeof(int) * 2 * ((size_t)nV + 1), s));

@@ -81,8 +81,9 @@ def test_grid_synthetic_and_slabs(oracle, pd):
     # z-slab build: assembled slabs == single build, bit for bit
     from meshode_b200 import capi
     parts = []
+    dV, dF = _t(V), _t(F)   # keep the device buffers alive across the raw-pointer calls
     for z0, z1 in ((0, 13), (13, 32), (32, 48)):
-        p = capi.template_create_slab(_t(V).data_ptr(), V.shape[0], _t(F).data_ptr(), F.shape[0], N, z0, z1,
+        p = capi.template_create_slab(dV.data_ptr(), V.shape[0], dF.data_ptr(), F.shape[0], N, z0, z1,
                                       torch.cuda.current_stream().cuda_stream)
         s64, s32, sidx = pd.GetGrid(p)
         full = s64.cpu().numpy()
