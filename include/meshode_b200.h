@@ -144,7 +144,7 @@ int mo_edges_backward(int param_id, int kind, const float* d_V, int nV, const in
 int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF,
                              const int* d_E, int nE, float* d_grad, mo_stream_t stream);
 
-/* ---- fused per-iteration loss (src/python/layers/*_loss_layer.py) --------------------- */
+/* ---- fused per-iteration loss (src/python/layers/{rigid,graph,graph2}_loss_layer.py) --------------------- */
 /* L = 0.5*sum(dist_fwd) + w_edge*0.5*sum(edge_fwd);  grad = mask*dist_bwd + w_edge*edge_bwd
  * (rigid_loss_layer.py:9-27 with w_edge = 1; graph_loss_layer.py:11-43 with w_edge =
  * rigidity^2 and mask_threshold = 0.5*0.03^2 on 0.5*dist_fwd; mask_threshold <= 0 disables

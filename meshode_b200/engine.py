@@ -104,8 +104,4 @@ class PairBatch:
         self.pids = []
 
 
-def shard_range(n_items, rank, world):
-    """Contiguous block partition of pair indices: pair i -> rank floor(i*world/n)."""
-    lo = (n_items * rank) // world
-    hi = (n_items * (rank + 1)) // world
-    return lo, hi
+from .sharding import shard_range  # noqa: E402,F401  (kept here for callers of engine.shard_range)

@@ -35,8 +35,8 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def _dev(t, dtype, cols, name):
-    """Validated device view of ``t`` ([n, cols], ``dtype``, contiguous)."""
+def _check(t, dtype, cols, name):
+    """Raises unless ``t`` is a contiguous [n, cols] tensor of ``dtype`` (the reference checks nothing)."""
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % name)
     if t.dtype != dtype:
@@ -45,6 +45,11 @@ def _dev(t, dtype, cols, name):
         raise ValueError("%s must have shape [n, %d], got %s" % (name, cols, tuple(t.shape)))
     if not t.is_contiguous():
         raise ValueError("%s must be contiguous" % name)
+
+
+def _dev(t, dtype, cols, name):
+    """Validated device view of ``t`` ([n, cols], ``dtype``, contiguous)."""
+    _check(t, dtype, cols, name)
     if t.is_cuda:
         return t
     return t.to(_device(), non_blocking=False)
@@ -89,6 +94,8 @@ def SolveLinear(tensorV, tensorF, tensorE, tensorRef, tensorGraphV, rigidity, wi
 # ---- template ----------------------------------------------------------------------------
 def InitializeDeformTemplate(tensorV, tensorF, symmetry, grid_resolution):
     """deform_params.cc:16-40 -> param_id (int)."""
+    _check(tensorV, torch.float32, 3, "tensorV")
+    _check(tensorF, torch.int32, 3, "tensorF")
     V = _dev(tensorV, torch.float32, 3, "tensorV")
     F = _dev(tensorF, torch.int32, 3, "tensorF").to(V.device)
     with torch.cuda.device(V.device):
@@ -147,6 +154,11 @@ def DistanceFieldLoss_forward_backward(tensorV, param_id):
 
 # ---- edge losses -------------------------------------------------------------------------
 def _edges(fn, kind, tensorV, tensorF, tensorE, param_id, out_rows):
+    _check(tensorV, torch.float32, 3, "tensorV")
+    if tensorF is not None:
+        _check(tensorF, torch.int32, 3, "tensorF")
+    if tensorE is not None:
+        _check(tensorE, torch.int32, 2, "tensorE")
     V = _dev(tensorV, torch.float32, 3, "tensorV")
     F = _dev(tensorF, torch.int32, 3, "tensorF").to(V.device) if tensorF is not None else None
     E = _dev(tensorE, torch.int32, 2, "tensorE").to(V.device) if tensorE is not None else None

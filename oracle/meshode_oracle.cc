@@ -640,10 +640,13 @@ void orc_rigid_adam(const double* grid, int N, float* V, int nV, const int* F, i
     const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), epsf = (float)eps;
     for (size_t i = 0; i < n3; ++i) {
       const float g = (gD[i] + gR[i]) * 1.0f;
-      m[i] = m[i] + w1 * (g - m[i]);                 // exp_avg.lerp_(grad, 1-beta1)
-      v[i] = v[i] * b2 + w2 * (g * g);               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+      // Operation order and FMA use follow what torch's own kernels compute (checked against
+      // torch 2.11 CPU in tests/test_oracle_kat.py): lerp is fma(weight, end - start, start),
+      // addcmul is fma(value * t1, t2, self), addcdiv is self + (value * t1) / t2.
+      m[i] = std::fmaf(w1, g - m[i], m[i]);              // exp_avg.lerp_(grad, 1-beta1)
+      v[i] = std::fmaf(w2 * g, g, v[i] * b2);            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
       const float denom = std::sqrt(v[i]) / bc2_sqrt + epsf;
-      V[i] = V[i] + (-step_size) * (m[i] / denom);   // param.addcdiv_(exp_avg, denom, value=-step_size)
+      V[i] = V[i] + ((-step_size) * m[i]) / denom;       // param.addcdiv_(exp_avg, denom, value=-step_size)
     }
   }
 }

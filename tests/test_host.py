@@ -1,0 +1,81 @@
+"""Host-side logic without a GPU: synthetic shape generator, OBJ I/O semantics, argument
+validation of the pyDeform mirror, and its loud failure when no CUDA device exists."""
+import os
+
+import numpy as np
+import pytest
+
+
+def test_synth_mesh_is_deterministic_closed_manifold():
+    from meshode_b200.synth import synth_mesh, synth_pair, unique_edges
+    V, F = synth_mesh(500, 3)
+    V2, F2 = synth_mesh(500, 3)
+    assert np.array_equal(V, V2) and np.array_equal(F, F2)
+    assert V.dtype == np.float32 and F.dtype == np.int32 and F.shape == (2 * 500 - 4, 3)
+    E = unique_edges(F)
+    assert E.shape[0] == 3 * 500 - 6                      # Euler: closed genus-0 triangulation
+    # every undirected edge is used by exactly two triangles, once per direction (oriented manifold)
+    d = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]])
+    key = d[:, 0].astype(np.int64) * 500 + d[:, 1]
+    assert np.unique(key).size == key.size
+    assert np.isin(d[:, 1].astype(np.int64) * 500 + d[:, 0], key).all()
+    # outward orientation: positive signed volume
+    a, b, c = (V[F[:, k]].astype(np.float64) for k in range(3))
+    assert np.einsum("ij,ij->i", a, np.cross(b, c)).sum() > 0
+    sV, sF, tV, tF = synth_pair(2, 300, 400)
+    assert sV.shape == (300, 3) and tV.shape == (400, 3) and sF.shape == (596, 3) and tF.shape == (796, 3)
+
+
+def test_obj_io_reference_semantics(tmp_path, meshes):
+    from meshode_b200.objio import read_obj, write_obj
+    p = tmp_path / "m.obj"
+    p.write_text("# comment\nvn 0 0 1\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvt 0 0\n"
+                 "f 1//1 2//1 3//1\nf 1/5/2 3/4/2 4/1/2 2/2/2\n\ng grp\nf 2 3 4\n")
+    V, F = read_obj(str(p))
+    assert V.dtype == np.float32 and F.dtype == np.int32
+    assert V.shape == (4, 3)
+    # leading index of a/b/c tokens, 1-based, first three tokens of a face (mesh.cc:14-45)
+    assert F.tolist() == [[0, 1, 2], [0, 2, 3], [1, 2, 3]]
+    q = tmp_path / "o.obj"
+    write_obj(str(q), meshes["cadTarV"], meshes["cadTarF"])
+    V2, F2 = read_obj(str(q))
+    assert np.array_equal(F2, meshes["cadTarF"])
+    assert np.allclose(V2, meshes["cadTarV"], rtol=1e-5, atol=0)   # "%.6g"-style text precision
+
+
+def test_pydeform_surface_matches_reference_names():
+    import pyDeform
+    names = ["LoadMesh", "LoadCadMesh", "SaveMesh", "InitializeDeformTemplate", "NormalizeByTemplate",
+             "DenormalizeByTemplate", "SolveLinear", "DistanceFieldLoss_forward", "DistanceFieldLoss_backward",
+             "RigidEdgeLoss_forward", "RigidEdgeLoss_backward", "StoreRigidityInformation", "CadEdgeLoss_forward",
+             "CadEdgeLoss_backward", "StoreCadInformation", "GraphEdgeLoss_forward", "GraphEdgeLoss_backward",
+             "StoreGraphInformation"]          # src/interface/pydeform.cc:15-37
+    for n in names:
+        assert callable(getattr(pyDeform, n)), n
+
+
+def test_pydeform_validates_and_fails_loudly_without_gpu():
+    torch = pytest.importorskip("torch")
+    from meshode_b200 import capi
+    from meshode_b200 import pyDeform as pd
+    V = torch.zeros((4, 3), dtype=torch.float32); F = torch.zeros((2, 3), dtype=torch.int32)
+    with pytest.raises(TypeError):
+        pd.InitializeDeformTemplate(V.double(), F, 0, 8)
+    with pytest.raises(TypeError):
+        pd.InitializeDeformTemplate(V, F.long(), 0, 8)
+    with pytest.raises(ValueError):
+        pd.DistanceFieldLoss_forward(torch.zeros((4, 2), dtype=torch.float32), 0)
+    with pytest.raises(ValueError):
+        pd.DistanceFieldLoss_forward(torch.zeros((3, 8), dtype=torch.float32).t()[:, :3], 0)
+    if capi.device_count() == 0:
+        with pytest.raises(capi.MeshodeError):          # no CPU fallback
+            pd.InitializeDeformTemplate(V, F, 0, 8)
+        with pytest.raises(capi.MeshodeError):
+            pd.DistanceFieldLoss_forward(V, 0)
+
+
+def test_golden_fixtures_are_self_consistent(meshes, golden):
+    assert meshes["tarV"].shape == (14762, 3) and meshes["tarF"].shape == (29532, 3)      # data/target.obj
+    assert meshes["srcV"].shape == (21542, 3) and meshes["srcF"].shape == (43100, 3)      # data/source.obj
+    assert golden["grid"].shape == (32, 32, 32) and golden["nearest"].min() >= 0
+    assert golden["nearest"].max() < meshes["tarF"].shape[0]
