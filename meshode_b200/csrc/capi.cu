@@ -56,7 +56,8 @@ Template* lookup(int pid) {
 void release(Template& T, cudaStream_t s = 0) {
   free_edges(T, s);
   dev_free(T.d_Vn, s); dev_free(T.d_F, s); dev_free(T.d_grid64, s); dev_free(T.d_grid32, s); dev_free(T.d_nearest, s);
-  dev_free(T.d_xf, s); dev_free(T.d_stats, s);
+  dev_free(T.d_xf, s); dev_free(T.d_stats, s); dev_free(T.d_cells, s);
+  T.d_cells = nullptr;
 }
 
 int allocate(Template& T, cudaStream_t s) {
@@ -195,6 +196,7 @@ int mo_template_copy_grid(int param_id, int direction, int z0, int z1, double* d
   const size_t off = (size_t)z0 * T->N * T->N, cnt = (size_t)(z1 - z0) * T->N * T->N;
   cudaStream_t s = (cudaStream_t)stream;
   if (cnt == 0) return MO_OK;
+  if (direction == 1 && T->d_cells) { dev_free(T->d_cells, s); T->d_cells = nullptr; }   // derived from grid_f32
   if (d_grid_f64)
     MO_CUDA(cudaMemcpyAsync(direction ? (void*)(T->d_grid64 + off) : (void*)(d_grid_f64 + off),
                             direction ? (const void*)(d_grid_f64 + off) : (const void*)(T->d_grid64 + off),

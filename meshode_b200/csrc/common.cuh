@@ -33,6 +33,7 @@ struct Template {
   int* d_csr_start = nullptr;   // [eV+1]
   int* d_csr_key = nullptr;     // [2*nEdges] 2*edge + side, ascending per vertex
   float* d_v0 = nullptr;        // [eV,3] vertices at store time (rest = V0[v1] - V0[v0])
+  float* d_cells = nullptr;     // [N^3][8] the eight corner values of every cell, one 32-byte record (deform engine; built on first use)
   unsigned* d_ell = nullptr;    // [ceil(ell_D/2)][eV] packed other endpoints per incident edge, built on first deform
   int ell_D = 0;
 };
