@@ -173,6 +173,33 @@ int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* 
 int mo_deform_adam_large(int dist_pid, int edge_pid, float* d_V, int nV, float w_edge, float mask_threshold,
                          int iters, double lr, double beta1, double beta2, double eps, mo_stream_t stream);
 
+/* ---- nearest vertex (src/python/layers/reverse_loss_layer.py:15-19) --------------------- */
+/* cKDTree(P).query(Q, k=1): for every query point Q[i] (float32 [nQ,3]) the index of the nearest
+ * point of P (float32 [nP,3]) into d_idx (int32 [nQ]) and, if d_dist2 != NULL, the squared distance
+ * (FP64, like cKDTree's double arithmetic).  Exact search; the lowest index wins exact ties. */
+int mo_nearest_vertex(const float* d_Q, int nQ, const float* d_P, int nP, int* d_idx, double* d_dist2,
+                      mo_stream_t stream);
+
+/* ---- the Ceres loss terms of the C++ drivers (src/lib/deformer.cc), FP64 ------------------ */
+enum { MO_CERES_EDGE = 0, MO_CERES_ADAPTIVE_EDGE = 1, MO_CERES_ROT_EDGE = 2 };
+/* Residual blocks EdgeLoss (src/lib/edgeloss.h:8-33), AdaptiveEdgeLoss (:35-62) or EdgeLossWithRot
+ * (:64-98) for nE edges: block e couples p1 = V[I[e,0]], p2 = V[I[e,1]] (and rot1 = R[I[e,0]], rot2 =
+ * R[I[e,1]] for kind ROT; d_R may be NULL otherwise) with rest vector d_rest[e] (Deformer passes
+ * v = V0[a] - V0[b], deformer.cc:44-49).  d_res receives [nE,3] ([nE,6] for ROT); d_jac, if not
+ * NULL, the Jacobian ceres::AutoDiffCostFunction would return: [nE,3,6] over (p1,p2), or [nE,6,12]
+ * over (p1,p2,rot1,rot2) for ROT, row-major. */
+int mo_ceres_edges(int kind, const double* d_V, const double* d_R, int nV, const int* d_I, const double* d_rest,
+                   int nE, double lambda, double* d_res, double* d_jac, mo_stream_t stream);
+/* What ceres::Problem::Evaluate returns for the problems of Deformer::Deform / DeformWithRot /
+ * DeformGraph (src/lib/deformer.cc:18-92, :94-171, :370-442): nV DistanceLoss blocks on the field
+ * of dist_param_id (src/lib/distanceloss.h:6-25; dist_param_id < 0 leaves them out) plus nE edge
+ * blocks of `kind`.  d_cost2[0] = 0.5*sum of squared distance residuals, d_cost2[1] = same for the
+ * edge residuals; d_gV [nV,3] and d_gR [nV,3] (ROT only) receive the gradient J^T r.  Any output
+ * may be NULL. */
+int mo_ceres_problem(int dist_param_id, int kind, const double* d_V, const double* d_R, int nV, const int* d_I,
+                     const double* d_rest, int nE, double lambda, double* d_cost2, double* d_gV, double* d_gR,
+                     mo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

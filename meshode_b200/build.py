@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmeshode_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
-SOURCES = ["sdf_build.cu", "sampler.cu", "edges.cu", "capi.cu", "deform.cu", "microbench.cu", "ceres_path.cu"]
+SOURCES = ["sdf_build.cu", "sampler.cu", "edges.cu", "capi.cu", "deform.cu", "microbench.cu", "nearest.cu", "ceres_path.cu"]
 
 
 def _nvcc():

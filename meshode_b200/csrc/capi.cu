@@ -375,6 +375,31 @@ int mo_deform_adam_large(int dist_pid, int edge_pid, float* d_V, int nV, float w
   return deform_adam_large(*TD, *TE, d_V, nV, w_edge, mask_threshold, iters, lr, beta1, beta2, eps, (cudaStream_t)stream);
 }
 
+int mo_ceres_edges(int kind, const double* d_V, const double* d_R, int nV, const int* d_I, const double* d_rest, int nE,
+                   double lambda, double* d_res, double* d_jac, mo_stream_t stream) {
+  MO_REQUIRE(kind == MO_CERES_EDGE || kind == MO_CERES_ADAPTIVE_EDGE || kind == MO_CERES_ROT_EDGE, "unknown Ceres edge kind");
+  MO_REQUIRE(nV >= 0 && nE >= 0, "negative size");
+  MO_REQUIRE(nE == 0 || (d_V && d_I && d_rest), "null pointer");
+  MO_REQUIRE(kind != MO_CERES_ROT_EDGE || nE == 0 || d_R, "EdgeLossWithRot needs the rotation parameters");
+  return ceres_edges(kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, d_res, d_jac, (cudaStream_t)stream);
+}
+
+int mo_ceres_problem(int dist_param_id, int kind, const double* d_V, const double* d_R, int nV, const int* d_I,
+                     const double* d_rest, int nE, double lambda, double* d_cost2, double* d_gV, double* d_gR,
+                     mo_stream_t stream) {
+  MO_REQUIRE(kind == MO_CERES_EDGE || kind == MO_CERES_ADAPTIVE_EDGE || kind == MO_CERES_ROT_EDGE, "unknown Ceres edge kind");
+  MO_REQUIRE(nV >= 0 && nE >= 0, "negative size");
+  MO_REQUIRE(nV == 0 || d_V, "null vertex pointer");
+  MO_REQUIRE(nE == 0 || (d_I && d_rest), "null edge pointer");
+  MO_REQUIRE(kind != MO_CERES_ROT_EDGE || nE == 0 || d_R, "EdgeLossWithRot needs the rotation parameters");
+  Template* TD = nullptr;
+  if (dist_param_id >= 0) {
+    TD = lookup(dist_param_id);
+    if (!TD) return MO_ERR_BAD_HANDLE;
+  }
+  return ceres_problem(TD, kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, d_cost2, d_gV, d_gR, (cudaStream_t)stream);
+}
+
 int mo_normalize_by_template(float* d_V, int n, int param_id, int inverse, mo_stream_t stream) {
   Template* T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;

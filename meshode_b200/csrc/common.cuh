@@ -86,6 +86,12 @@ int edges_backward_atomic(const Template& T, int kind, const float* d_V, int nV,
 int loss_fused(const Template& TD, const Template* TE, const float* d_V, int nV, float w_edge, float mask_thr,
                double* d_loss, float* d_grad, cudaStream_t s);
 
+// ceres_path.cu
+int ceres_edges(int kind, const double* d_V, const double* d_R, int nV, const int* d_I, const double* d_rest, int nE,
+                double lambda, double* d_res, double* d_jac, cudaStream_t s);
+int ceres_problem(const Template* TD, int kind, const double* d_V, const double* d_R, int nV, const int* d_I,
+                  const double* d_rest, int nE, double lambda, double* d_cost2, double* d_gV, double* d_gR, cudaStream_t s);
+
 // deform.cu
 int deform_batch_adam(Template* const* TD, Template* const* TE, float* const* h_V, int B, int iters, double lr,
                       double beta1, double beta2, double eps, cudaStream_t s);

@@ -255,3 +255,63 @@ def SetGrid(param_id, g64, g32, idx, z0=0, z1=None):
     z1 = N if z1 is None else z1
     capi.check(capi.lib().mo_template_copy_grid(pid, 1, z0, z1, _ptr(g64), _ptr(g32), _ptr(idx),
                                                 torch.cuda.current_stream().cuda_stream))
+
+
+def NearestVertex(tensorQ, tensorP, return_dist2=False):
+    """Additive (ReverseLossLayer): index [nQ] int32 of the nearest row of ``tensorP`` for every row of
+    ``tensorQ`` -- scipy's cKDTree(P).query(Q, k=1) on the GPU, exact, FP64 distances."""
+    _check(tensorQ, torch.float32, 3, "tensorQ")
+    _check(tensorP, torch.float32, 3, "tensorP")
+    Q = _dev(tensorQ, torch.float32, 3, "tensorQ")
+    P = _dev(tensorP, torch.float32, 3, "tensorP").to(Q.device)
+    idx = torch.empty(Q.shape[0], dtype=torch.int32, device=Q.device)
+    d2 = torch.empty(Q.shape[0], dtype=torch.float64, device=Q.device) if return_dist2 else None
+    with torch.cuda.device(Q.device):
+        capi.check(capi.lib().mo_nearest_vertex(_ptr(Q), Q.shape[0], _ptr(P), P.shape[0], _ptr(idx),
+                                                d2.data_ptr() if return_dist2 else 0, _stream(Q)))
+    return (_back(idx, tensorQ), _back(d2, tensorQ)) if return_dist2 else _back(idx, tensorQ)
+
+
+# ---- the Ceres loss terms of the C++ drivers (additive: the reference has no Python binding for them) ----
+def _f64(t, cols, name, device=None):
+    _check(t, torch.float64, cols, name)
+    return t if t.is_cuda else t.to(device if device is not None else _device())
+
+
+def CeresEdges(kind, V, R, I, rest, lam, want_jacobian=False):
+    """Residual blocks EdgeLoss / AdaptiveEdgeLoss / EdgeLossWithRot (src/lib/edgeloss.h) for the edge list
+    ``I`` [e,2]: returns residuals [e,3] ([e,6] for capi.CERES_ROT_EDGE) and, optionally, the autodiff
+    Jacobians [e,3,6] / [e,6,12].  float64 tensors."""
+    V = _f64(V, 3, "V")
+    dev = V.device
+    R = _f64(R, 3, "R", dev) if R is not None else None
+    _check(I, torch.int32, 2, "I")
+    I = I.to(dev)
+    rest = _f64(rest, 3, "rest", dev)
+    rot = kind == capi.CERES_ROT_EDGE
+    res = torch.empty((I.shape[0], 6 if rot else 3), dtype=torch.float64, device=dev)
+    jac = torch.empty((I.shape[0], 6, 12) if rot else (I.shape[0], 3, 6), dtype=torch.float64, device=dev) if want_jacobian else None
+    with torch.cuda.device(dev):
+        capi.check(capi.lib().mo_ceres_edges(int(kind), _ptr(V), _ptr(R), V.shape[0], _ptr(I), _ptr(rest), I.shape[0],
+                                             float(lam), _ptr(res), _ptr(jac), _stream(V)))
+    return (res, jac) if want_jacobian else res
+
+
+def CeresProblem(dist_param_id, kind, V, R, I, rest, lam):
+    """Cost and gradient of the Deformer problems (src/lib/deformer.cc): returns
+    (cost_distance, cost_edges) as a float64 [2] tensor, gV [n,3] and gR [n,3] (None unless ROT)."""
+    V = _f64(V, 3, "V")
+    dev = V.device
+    rot = kind == capi.CERES_ROT_EDGE
+    R = _f64(R, 3, "R", dev) if R is not None else None
+    _check(I, torch.int32, 2, "I")
+    I = I.to(dev)
+    rest = _f64(rest, 3, "rest", dev)
+    cost = torch.empty(2, dtype=torch.float64, device=dev)
+    gV = torch.empty_like(V)
+    gR = torch.empty_like(V) if rot else None
+    with torch.cuda.device(dev):
+        capi.check(capi.lib().mo_ceres_problem(_pid(dist_param_id) if dist_param_id is not None else -1, int(kind), _ptr(V),
+                                               _ptr(R), V.shape[0], _ptr(I), _ptr(rest), I.shape[0], float(lam),
+                                               _ptr(cost), _ptr(gV), _ptr(gR), _stream(V)))
+    return cost, gV, gR

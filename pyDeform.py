@@ -3,4 +3,4 @@ import torch  # noqa: F401  (the reference requires torch to be imported first; 
 
 from meshode_b200.pyDeform import *  # noqa: F401,F403
 from meshode_b200.pyDeform import (DestroyTemplate, DistanceFieldLoss_forward_backward, EdgeLoss_backward_atomic,  # noqa: F401
-                                   GetGrid, GetTemplateInfo, LossForwardBackward, SetGrid)
+                                   GetGrid, GetTemplateInfo, LossForwardBackward, NearestVertex, SetGrid)
