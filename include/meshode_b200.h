@@ -154,6 +154,8 @@ int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, c
 int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* d_V, int nV, float w_edge,
                              float mask_threshold, double* d_loss, float* d_grad, mo_stream_t stream);
 
+enum { MO_DEFORM_EXACT = 1 };
+
 /* ---- whole optimisation loops (src/python/rigid_deform.py:32-41) ----------------------- */
 /* For each of B independent pairs: `iters` iterations of
  *     grad = DistanceFieldLoss_backward(V, dist_pid) + {Rigid,Graph}EdgeLoss_backward(V, edge_pid)
@@ -163,10 +165,15 @@ int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* 
  * memory.  h_dist_pids / h_edge_pids are HOST arrays of B param_ids (they may be equal, as in
  * rigid_loss_layer.py, or differ, as in graph_loss2_layer.py:18-19); h_dV is a HOST array of B
  * device pointers to normalised float32 [nV_i,3] vertices, updated in place.  Edges (RIGID or
- * GRAPH) must have been stored with mo_edges_store for nV_i <= 6144 vertices.  Bit-identical
- * to running the per-call entry points and Adam in float32 on the CPU. */
+ * GRAPH) must have been stored with mo_edges_store for nV_i <= 6144 vertices.
+ * flags = MO_DEFORM_EXACT: bit-identical to running the per-call entry points and Adam in float32 on
+ * the CPU (edge terms accumulated in the reference's order); this is what the parity gates and
+ * bench.py use.  flags = 0 (fast, opt-in): the edge term is summed over distinct neighbours on
+ * displacements U = V - V0 -- mathematically the same sum, one gather per neighbour, ~1e-10 per
+ * term away from the reference's float32 order; Adam amplifies that to ~2e-4 Chamfer after 10 000
+ * iterations, exactly what a 1-ulp change of the input does to the exact loop (tools/chaos_probe.py). */
 int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* const* h_dV, int B, int iters,
-                         double lr, double beta1, double beta2, double eps, mo_stream_t stream);
+                         double lr, double beta1, double beta2, double eps, int flags, mo_stream_t stream);
 /* Same loop for one pair of any size (state in HBM/L2, two launches per iteration), with the
  * graph layer's options: edge weight (rigidity^2) and distance-gradient mask threshold
  * (graph_loss_layer.py:18,40-42; mask_threshold <= 0 disables the mask). */

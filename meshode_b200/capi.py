@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmeshode_b200.so")
 MO_OK = 0
 EDGES_RIGID, EDGES_GRAPH, EDGES_CAD = 0, 1, 2
 CERES_EDGE, CERES_ADAPTIVE_EDGE, CERES_ROT_EDGE = 0, 1, 2
+DEFORM_EXACT = 1
 
 _vp, _i, _d, _f = C.c_void_p, C.c_int, C.c_double, C.c_float
 _ip, _dp, _ullp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)
@@ -43,7 +44,7 @@ SIGNATURES = {
     "mo_edges_backward": [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp],
     "mo_edges_backward_atomic": [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp],
     "mo_loss_forward_backward": [_i, _i, _vp, _i, _f, _f, _vp, _vp, _vp],
-    "mo_deform_batch_adam": [_ip, _ip, C.POINTER(_vp), _i, _i, _d, _d, _d, _d, _vp],
+    "mo_deform_batch_adam": [_ip, _ip, C.POINTER(_vp), _i, _i, _d, _d, _d, _d, _i, _vp],
     "mo_deform_adam_large": [_i, _i, _vp, _i, _f, _f, _i, _d, _d, _d, _d, _vp],
     "mo_nearest_vertex": [_vp, _i, _vp, _i, _vp, _vp, _vp],
     "mo_ceres_edges": [_i, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp],

@@ -352,7 +352,7 @@ int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* 
 
 
 int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* const* h_dV, int B, int iters, double lr,
-                         double beta1, double beta2, double eps, mo_stream_t stream) {
+                         double beta1, double beta2, double eps, int flags, mo_stream_t stream) {
   MO_REQUIRE(B >= 0 && iters >= 0, "negative count");
   MO_REQUIRE(B == 0 || (h_dist_pids && h_edge_pids && h_dV), "null pointer");
   std::vector<Template*> td(B), te(B);
@@ -362,7 +362,7 @@ int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* 
     if (!td[i] || !te[i]) return MO_ERR_BAD_HANDLE;
     MO_REQUIRE(h_dV[i] != nullptr, "null vertex pointer");
   }
-  return deform_batch_adam(td.data(), te.data(), h_dV, B, iters, lr, beta1, beta2, eps, (cudaStream_t)stream);
+  return deform_batch_adam(td.data(), te.data(), h_dV, B, iters, lr, beta1, beta2, eps, flags, (cudaStream_t)stream);
 }
 
 int mo_deform_adam_large(int dist_pid, int edge_pid, float* d_V, int nV, float w_edge, float mask_threshold, int iters,

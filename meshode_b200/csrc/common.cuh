@@ -36,6 +36,8 @@ struct Template {
   float* d_cells = nullptr;     // [N^3][8] the eight corner values of every cell, one 32-byte record (deform engine; built on first use)
   unsigned* d_ell = nullptr;    // [ceil(ell_D/2)][eV] packed other endpoints per incident edge, built on first deform
   int ell_D = 0;
+  unsigned* d_nbr = nullptr;    // [nbr_W][eV] distinct neighbours with multiplicities (fast deform loop), built on first use
+  int nbr_W = 0;
 };
 
 // Stream-ordered allocation from the device's default memory pool (release threshold raised so
@@ -94,7 +96,7 @@ int ceres_problem(const Template* TD, int kind, const double* d_V, const double*
 
 // deform.cu
 int deform_batch_adam(Template* const* TD, Template* const* TE, float* const* h_V, int B, int iters, double lr,
-                      double beta1, double beta2, double eps, cudaStream_t s);
+                      double beta1, double beta2, double eps, int flags, cudaStream_t s);
 int deform_adam_large(Template& TD, Template& TE, float* d_V, int nV, float w_edge, float mask_thr, int iters, double lr,
                       double beta1, double beta2, double eps, cudaStream_t s);
 

@@ -255,9 +255,9 @@ __global__ void __launch_bounds__(kBlock) k_loss_fused(const float* __restrict__
 
 void free_edges(Template& T, cudaStream_t s) {
   dev_free(T.d_ev, s); dev_free(T.d_rest, s); dev_free(T.d_lambda, s); dev_free(T.d_csr_start, s); dev_free(T.d_csr_key, s);
-  dev_free(T.d_v0, s); dev_free(T.d_ell, s);
+  dev_free(T.d_v0, s); dev_free(T.d_ell, s); dev_free(T.d_nbr, s);
   T.d_ev = nullptr; T.d_rest = nullptr; T.d_lambda = nullptr; T.d_csr_start = nullptr; T.d_csr_key = nullptr;
-  T.d_v0 = nullptr; T.d_ell = nullptr; T.ell_D = 0;
+  T.d_v0 = nullptr; T.d_ell = nullptr; T.ell_D = 0; T.d_nbr = nullptr; T.nbr_W = 0;
   T.kind = MO_EDGES_NONE; T.nEdges = 0;
 }
 
@@ -279,6 +279,7 @@ int edges_store(Template& T, int kind, const float* d_V, int nV, const int* d_F,
     MO_CUDA(dev_alloc(&T.d_v0, 3 * (size_t)std::max(nV, 1), s));
   }
   if (T.d_ell) { dev_free(T.d_ell, s); T.d_ell = nullptr; T.ell_D = 0; }
+  if (T.d_nbr) { dev_free(T.d_nbr, s); T.d_nbr = nullptr; T.nbr_W = 0; }
   if (nV > 0) MO_CUDA(cudaMemcpyAsync(T.d_v0, d_V, sizeof(float) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, s));
   T.kind = kind; T.nEdges = nEdges; T.eV = nV; T.eF = nF; T.eE = nE;
   int* deg = nullptr;   // [nV] degree + [nV] fill cursor

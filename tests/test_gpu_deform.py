@@ -30,7 +30,7 @@ def test_persistent_engine_bit_exact(oracle, pd, n_src, n_tar, N, iters):
     assert np.array_equal(batch.V[0].cpu().numpy(), src_n)
     rest = oracle.store_rigid(src_n, srcF)
     ref, _ = oracle.rigid_adam(tmpl.grid, src_n, srcF, rest, iters, 1e-3)
-    batch.deform(iters=iters, lr=1e-3)
+    batch.deform(iters=iters, lr=1e-3, exact=True)
     got = batch.V[0].cpu().numpy()
     # north_star gate: Chamfer <= 1e-4 (normalised units); achieved: identical bits
     assert _chamfer(got, ref) <= 1e-4
@@ -48,10 +48,10 @@ def test_batch_of_pairs_matches_single(oracle, pd):
     pairs = [tuple(torch.from_numpy(a) for a in synth_pair(i, 700 + 50 * i, 800)) for i in range(5)]
     iters = 120
     b_all = engine.PairBatch(pairs, grid_resolution=32)
-    b_all.deform(iters=iters)
+    b_all.deform(iters=iters, exact=True)
     for i, p in enumerate(pairs):
         b1 = engine.PairBatch([p], grid_resolution=32)
-        b1.deform(iters=iters)
+        b1.deform(iters=iters, exact=True)
         assert torch.equal(b1.V[0], b_all.V[i])
         b1.release()
     # and against the oracle for one of them
@@ -69,7 +69,7 @@ def test_large_mesh_loop_cfg1(meshes, oracle, pd):
     N, iters = 32, 25
     p = [torch.from_numpy(meshes[k]) for k in ("srcV", "srcF", "tarV", "tarF")]
     batch = engine.PairBatch([tuple(p)], grid_resolution=N)
-    batch.deform(iters=iters)
+    batch.deform(iters=iters, exact=True)
     tmpl = oracle.Template(meshes["tarV"], meshes["tarF"], N)
     src_n = oracle.normalize_by_template(meshes["srcV"], tmpl.scale, tmpl.trans)
     ref, _ = oracle.rigid_adam(tmpl.grid, src_n, meshes["srcF"], oracle.store_rigid(src_n, meshes["srcF"]), iters, 1e-3)
@@ -77,3 +77,50 @@ def test_large_mesh_loop_cfg1(meshes, oracle, pd):
     assert _chamfer(got, ref) <= 1e-4
     assert np.array_equal(got, ref), "max |dV| = %g" % np.abs(got - ref).max()
     batch.release()
+
+
+@pytest.mark.parametrize("n_src,n_tar,N,iters", [(1500, 1200, 32, 300), (5000, 5000, 64, 400)])
+def test_fast_engine_is_at_the_rounding_sensitivity_floor(oracle, pd, n_src, n_tar, N, iters):
+    """The opt-in fast loop (exact=False) sums the edge term over distinct neighbours on displacements:
+    mathematically the reference's sum, not its float32 order.  Adam's normalised steps make the
+    trajectory chaotic at the 1e-4 level -- moving every start coordinate by ONE ulp changes the exact
+    loop's result by the same amount (tools/chaos_probe.py: Chamfer ~1.9e-4 after 10 000 iterations) --
+    so the fast loop cannot meet the 1e-4 Chamfer gate against the CPU and is NOT the default; this
+    test pins it to that sensitivity floor: no further from the oracle than the oracle is from itself
+    under a 1-ulp perturbation (x3 margin)."""
+    from meshode_b200 import engine
+    from meshode_b200.synth import synth_pair
+    srcV, srcF, tarV, tarF = synth_pair(3, n_src, n_tar)
+    P = (torch.from_numpy(srcV), torch.from_numpy(srcF), torch.from_numpy(tarV), torch.from_numpy(tarF))
+    tmpl = oracle.Template(tarV, tarF, N)
+    src_n = oracle.normalize_by_template(srcV, tmpl.scale, tmpl.trans)
+    rest = oracle.store_rigid(src_n, srcF)
+    ref, _ = oracle.rigid_adam(tmpl.grid, src_n, srcF, rest, iters, 1e-3)
+    bumped, _ = oracle.rigid_adam(tmpl.grid, np.nextafter(src_n, np.float32(2.0)), srcF, rest, iters, 1e-3)
+    floor = _chamfer(bumped, ref)
+    fast = engine.PairBatch([P], grid_resolution=N)
+    fast.deform(iters=iters, lr=1e-3, exact=False)
+    got = fast.V[0].cpu().numpy()
+    assert np.abs(ref - src_n).max() > 1e-3
+    cham = _chamfer(got, ref)
+    print("fast vs oracle after %d iterations: chamfer %.3g (1-ulp sensitivity floor %.3g), max |dV| %.3g" %
+          (iters, cham, floor, np.abs(got - ref).max()))
+    assert cham <= max(3.0 * floor, 2e-5)
+    assert cham <= 5e-4
+    fast.release()
+
+
+def test_fast_and_exact_agree_over_a_few_iterations(oracle, pd):
+    """Before rounding differences are amplified the two loops coincide to float32 resolution."""
+    from meshode_b200 import engine
+    from meshode_b200.synth import synth_pair
+    srcV, srcF, tarV, tarF = synth_pair(9, 3000, 2500)
+    P = (torch.from_numpy(srcV), torch.from_numpy(srcF), torch.from_numpy(tarV), torch.from_numpy(tarF))
+    a = engine.PairBatch([P], grid_resolution=48)
+    b = engine.PairBatch([P], grid_resolution=48)
+    a.deform(iters=3, exact=True)
+    b.deform(iters=3, exact=False)
+    d = (a.V[0] - b.V[0]).abs()
+    # Adam's first steps are +-lr per coordinate; a gradient at the sign threshold may flip one of them
+    assert (d <= 1e-6).float().mean().item() > 0.995 and d.max().item() <= 6.1e-3
+    a.release(); b.release()
