@@ -33,7 +33,7 @@ SIGNATURES = {
     "mo_template_grid": [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "mo_template_copy_grid": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mo_template_vertices": [_i, C.POINTER(_vp)],
-    "mo_template_build_stats": [_i, _vp, _ullp, _ullp, _ullp],
+    "mo_template_build_stats": [_i, _vp, _ullp, _ullp, _ullp, _ullp],
     "mo_normalize_by_template": [_vp, _i, _i, _i, _vp],
     "mo_distance_forward": [_vp, _i, _i, _vp, _vp],
     "mo_distance_backward": [_vp, _i, _i, _vp, _vp],
@@ -138,6 +138,6 @@ def template_vertices(pid):
 
 
 def template_build_stats(pid, stream=0):
-    a, b, c = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
-    check(lib().mo_template_build_stats(int(pid), stream, C.byref(a), C.byref(b), C.byref(c)))
-    return {"fp32_tests": a.value, "fp64_tests": b.value, "cull_tests": c.value}
+    a, b, c, d = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+    check(lib().mo_template_build_stats(int(pid), stream, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+    return {"fp32_tests": a.value, "fp64_tests": b.value, "cull_tests": c.value, "sphere_tests": d.value}

@@ -69,7 +69,7 @@ int allocate(Template& T, cudaStream_t s) {
   MO_CUDA(dev_alloc(&T.d_grid32, nvox, s));
   MO_CUDA(dev_alloc(&T.d_nearest, nvox, s));
   MO_CUDA(dev_alloc(&T.d_xf, 4, s));
-  MO_CUDA(dev_alloc(&T.d_stats, 4, s));
+  MO_CUDA(dev_alloc(&T.d_stats, 8, s));
   return MO_OK;
 }
 
@@ -220,15 +220,16 @@ int mo_template_vertices(int param_id, const double** d_Vn) {
 }
 
 int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long* fp32_tests, unsigned long long* fp64_tests,
-                            unsigned long long* cull_tests) {
+                            unsigned long long* cull_tests, unsigned long long* sphere_tests) {
   Template* T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
-  unsigned long long h[4];
+  unsigned long long h[8];
   MO_CUDA(cudaMemcpyAsync(h, T->d_stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   MO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   if (fp32_tests) *fp32_tests = h[0];
   if (fp64_tests) *fp64_tests = h[1];
   if (cull_tests) *cull_tests = h[2];
+  if (sphere_tests) *sphere_tests = h[4];
   if (h[3]) {
     set_error("template holds invalid input: " + std::string((h[3] & 1) ? "[face index out of range] " : "") +
               ((h[3] & 2) ? "[non-finite vertex] " : "") + ((h[3] & 4) ? "[edge index out of range]" : ""));

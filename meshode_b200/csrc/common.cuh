@@ -23,7 +23,7 @@ struct Template {
   float* d_grid32 = nullptr;    // [N^3] (float) of the above
   int* d_nearest = nullptr;     // [N^3] nearest triangle (igl's I)
   double* d_xf = nullptr;       // [4] scale, trans.x, trans.y, trans.z  (params.scale / params.trans)
-  unsigned long long* d_stats = nullptr;   // [4] fp32 tests, fp64 tests, cull tests, error bits
+  unsigned long long* d_stats = nullptr;   // [5] fp32 tests, fp64 tests, cull tests, error bits, sphere pre-tests
   // one edge set per template (params.edge_offset / edge_lambda)
   int kind = MO_EDGES_NONE;
   int eV = 0, eF = 0, eE = 0, nEdges = 0;

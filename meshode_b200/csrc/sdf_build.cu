@@ -27,12 +27,14 @@
 namespace mo {
 namespace {
 
-constexpr int kTile = 8;          // voxels per tile edge
+constexpr int kTile = 8;          // voxels per tile edge in x and y
+constexpr int kTileZ = 4;         // voxels per tile in z: 8 warps per CTA, two CTAs per SM hide each other's barriers
 constexpr int kCellVox = 4;       // voxels per bin-cell edge
-constexpr int kWarps = 16;
+constexpr int kWarps = kTile * kTile * kTileZ / 32;
 constexpr int kThreads = kWarps * 32;
-constexpr int kCap = 2048;        // triangle records staged per chunk (64 B each)
-constexpr int kMaxRanges = 2048;  // cell ranges collected per pass
+constexpr int kCtasPerSm = 2;
+constexpr int kCap = 768;         // triangle records staged per chunk (64 B record + 16 B bounding sphere each)
+constexpr int kMaxRanges = 1024;  // cell ranges collected per pass
 constexpr int kListCap = 12;      // per-lane queue of FP64 candidates
 
 // |q_fp32 - q_exact| <= kA * |p-a|^2 + kB for coordinates inside the unit cube: record
@@ -42,12 +44,13 @@ constexpr float kErrA = 1.2e-5f;
 constexpr float kErrB = 1.2e-9f;
 
 struct SdfArgs {
-  int N, nc, ntile, tz0, z0, z1;
+  int N, nc, ntile, ntz, tz0, z0, z1;
   float cs;                       // cell size in normalised units
   const unsigned* max_ext;        // bit pattern of the largest triangle AABB extent
   const int* cell_start;          // [ncell+1]
   const unsigned* cell_bb;        // [ncell*6] ordered-uint lo xyz, hi xyz
   const float4* rec32;            // [nF*4] cell-sorted FP32 records
+  const float4* sph;              // [nF] cell-sorted bounding spheres (centre, radius rounded up)
   const double* rec64;            // [nF*9] cell-sorted FP64 vertices
   const int* tri_id;              // [nF] cell-sorted -> original triangle index
   double* grid64;
@@ -182,8 +185,8 @@ __global__ void k_scan(const int* __restrict__ in, int* __restrict__ out, int n)
 
 __global__ void k_tri_fill(const double* __restrict__ Vn, const int* __restrict__ F, int nF,
                            const int* __restrict__ tri_cell, const int* __restrict__ cell_start,
-                           int* __restrict__ cell_fill, float4* __restrict__ rec32, double* __restrict__ rec64,
-                           int* __restrict__ tri_id) {
+                           int* __restrict__ cell_fill, float4* __restrict__ rec32, float4* __restrict__ sph,
+                           double* __restrict__ rec64, int* __restrict__ tri_id) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nF) return;
   const int c = tri_cell[t];
@@ -221,6 +224,23 @@ __global__ void k_tri_fill(const double* __restrict__ Vn, const int* __restrict_
   rec32[4 * (size_t)slot + 1] = make_float4((float)ab[0], (float)ab[1], (float)ab[2], (float)e12);
   rec32[4 * (size_t)slot + 2] = make_float4((float)ac[0], (float)ac[1], (float)ac[2], (float)e22);
   rec32[4 * (size_t)slot + 3] = make_float4(r3x, isinf(i11) ? 0.f : i11, isinf(i22) ? 0.f : i22, isinf(ibc) ? 0.f : ibc);
+  // bounding sphere about the centroid; the radius absorbs the float rounding of the centre
+  {
+    double cx[3], r2 = 0.0;
+    float cf[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { cx[j] = (a[j] + b[j] + cc[j]) * (1.0 / 3.0); cf[j] = (float)cx[j]; }
+    const double* vs[3] = {a, b, cc};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { const double d = vs[k][j] - (double)cf[j]; d2 += d * d; }
+      r2 = fmax(r2, d2);
+    }
+    // + 2e-7: float rounding of the query point (<= 5.2e-8) and of the centre, with margin
+    sph[slot] = make_float4(cf[0], cf[1], cf[2], __double2float_ru(sqrt(r2) * 1.000001 + 2e-7));
+  }
   tri_id[slot] = t;
 }
 
@@ -346,6 +366,7 @@ struct LaneState {
   double best64;   // exact minimum so far
   int best_id;     // its original triangle index (lowest on exact ties)
   float ub;        // rigorous FP32 upper bound of the exact minimum
+  float sub;       // upper bound of sqrt(ub) (for the bounding-sphere pre-test)
   int cnt;         // queued FP64 candidates
   unsigned n64;
 };
@@ -363,6 +384,7 @@ __device__ __forceinline__ void flush_queue(LaneState& st, const int* s_lid, con
   }
   st.cnt = 0;
   if (st.best_id >= 0) st.ub = fminf(st.ub, __double2float_ru(st.best64));
+  st.sub = __fsqrt_ru(st.ub);
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -371,10 +393,11 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_rec = reinterpret_cast<float4*>(smem_raw);                 // kCap*4
-  int* s_gidx = reinterpret_cast<int*>(s_rec + kCap * 4);              // kCap
+  float4* s_sph = s_rec + kCap * 4;                                    // kCap
+  int* s_gidx = reinterpret_cast<int*>(s_sph + kCap);                  // kCap
   int* s_lid = s_gidx + kCap;                                          // kListCap*kThreads
   float* s_lq = reinterpret_cast<float*>(s_lid + kListCap * kThreads); // kListCap*kThreads
   int* s_rstart = reinterpret_cast<int*>(s_lq + kListCap * kThreads);  // kMaxRanges
@@ -382,14 +405,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
   int* s_roff = s_rcnt + kMaxRanges;
   __shared__ int s_nr, s_total;
   __shared__ unsigned s_ub[2];
-  __shared__ unsigned long long s_stats[3];
+  __shared__ unsigned long long s_stats[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = A.N, nc = A.nc;
-  const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile, tz = A.tz0 + blockIdx.x / (A.ntile * A.ntile);
+  const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile, tz = A.tz0 + blockIdx.x / (A.ntile * A.ntile);   // tz in units of kTileZ
 
   // this lane's voxel; the warp owns a 4x4x2 block of the tile
-  const int bx = tx * kTile + (warp & 1) * 4, by = ty * kTile + ((warp >> 1) & 1) * 4, bz = tz * kTile + (warp >> 2) * 2;
+  const int bx = tx * kTile + (warp & 1) * 4, by = ty * kTile + ((warp >> 1) & 1) * 4, bz = tz * kTileZ + (warp >> 2) * 2;
   const int vx = bx + (lane & 3), vy = by + ((lane >> 2) & 3), vz = bz + (lane >> 4);
   const bool valid = vx < N && vy < N && vz < N && vz >= A.z0 && vz < A.z1;
   const double invN = 1.0 / (double)N;
@@ -400,21 +423,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
   const float Rw = (float)(2.1795 * invN * 1.0001);   // half diagonal of the 3x3x1-interval sample box
 
   // tile sample box (clipped to the grid and the slab)
-  const float tlo[3] = {(float)(tx * kTile * invN), (float)(ty * kTile * invN), (float)(max(tz * kTile, A.z0) * invN)};
+  const float tlo[3] = {(float)(tx * kTile * invN), (float)(ty * kTile * invN), (float)(max(tz * kTileZ, A.z0) * invN)};
   const float thi[3] = {(float)(min(tx * kTile + kTile - 1, N - 1) * invN), (float)(min(ty * kTile + kTile - 1, N - 1) * invN),
-                        (float)(min(min(tz * kTile + kTile - 1, N - 1), A.z1 - 1) * invN)};
+                        (float)(min(min(tz * kTileZ + kTileZ - 1, N - 1), A.z1 - 1) * invN)};
 
   LaneState st;
-  st.best64 = DBL_MAX; st.best_id = -1; st.ub = __int_as_float(0x7f800000); st.cnt = 0; st.n64 = 0;
-  unsigned n32 = 0, ncull = 0;
+  st.best64 = DBL_MAX; st.best_id = -1; st.ub = __int_as_float(0x7f800000); st.sub = st.ub; st.cnt = 0; st.n64 = 0;
+  unsigned n32 = 0, ncull = 0, nsph = 0;
   float thr_w = __int_as_float(0x7f800000);
   float ub_cta = __int_as_float(0x7f800000);
   const float max_ext = __uint_as_float(*A.max_ext);
-  if (tid < 3) s_stats[tid] = 0ull;
+  if (tid < 4) s_stats[tid] = 0ull;
   if (tid < 2) s_ub[tid] = 0u;
   int par = 0;
 
-  const int cbx = 2 * tx, cby = 2 * ty, cbz = 2 * tz;   // the tile's 2x2x2 cell block
+  constexpr int kCz = kTileZ / kCellVox;                // cells per tile in z
+  const int cbx = 2 * tx, cby = 2 * ty, cbz = kCz * tz;   // the tile's 2 x 2 x kCz cell block
   for (int r = 0; r <= nc; ++r) {
     if (r >= 1) {
       const float lb = (float)(r - 1) * A.cs - max_ext;   // nothing binned in ring >= r is closer than this
@@ -423,12 +447,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
     if (r >= 1) {   // ring r-1 already enclosed the whole cell grid
       const int q = r - 1;
       if (cbx - q <= 0 && cby - q <= 0 && cbz - q <= 0 && cbx + 1 + q >= nc - 1 && cby + 1 + q >= nc - 1 &&
-          cbz + 1 + q >= nc - 1)
+          cbz + kCz - 1 + q >= nc - 1)
         break;
     }
-    const int side = 2 + 2 * r;
+    const int side = 2 + 2 * r, sidez = kCz + 2 * r;
     const int x0 = cbx - r, y0 = cby - r, z0c = cbz - r;
-    const int nenum = side * side * side;
+    const int nenum = side * side * sidez;
     for (int base = 0; base < nenum; base += kMaxRanges) {
       __syncthreads();
       if (tid == 0) { s_nr = 0; s_total = 0; }
@@ -436,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
       const int lim = min(nenum, base + kMaxRanges);
       for (int i = base + tid; i < lim; i += kThreads) {
         const int ix = i % side, iy = (i / side) % side, iz = i / (side * side);
-        if (r > 0 && ix > 0 && ix < side - 1 && iy > 0 && iy < side - 1 && iz > 0 && iz < side - 1) continue;
+        if (r > 0 && ix > 0 && ix < side - 1 && iy > 0 && iy < side - 1 && iz > 0 && iz < sidez - 1) continue;
         const int cx = x0 + ix, cy = y0 + iy, cz = z0c + iz;
         if ((unsigned)cx >= (unsigned)nc || (unsigned)cy >= (unsigned)nc || (unsigned)cz >= (unsigned)nc) continue;
         const int c = (cz * nc + cy) * nc + cx;
@@ -466,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
             const int g = start + (rec - off);
             s_rec[(rec - cb) * 4 + part] = __ldg(&A.rec32[4 * (size_t)g + part]);
             if (part == 0) s_gidx[rec - cb] = g;
+            if (part == 1) s_sph[rec - cb] = __ldg(&A.sph[g]);
           }
         }
         __syncthreads();
@@ -479,10 +504,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
           const float qc = tri_q(s_rec[jr * 4], s_rec[jr * 4 + 1], s_rec[jr * 4 + 2], s_rec[jr * 4 + 3], wcx, wcy, wcz, ec);
           unsigned m = __ballot_sync(0xffffffffu, has && (qc - ec <= thr_w));
           ncull += has ? 1u : 0u;
-          n32 += valid ? (unsigned)__popc(m) : 0u;
+          nsph += valid ? (unsigned)__popc(m) : 0u;
           while (m) {
             const int jj = b + __ffs(m) - 1;
             m &= m - 1;
+            // per-voxel pre-test against the triangle's bounding sphere: |p - c| - rho is a lower bound of
+            // the distance; if it exceeds every lane's upper bound the exact test is skipped for the warp
+            const float4 sp = s_sph[jj];
+            const float dx = px - sp.x, dy = py - sp.y, dz = pz - sp.z;
+            const float dc2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float reach = st.sub + sp.w;
+            if (!__any_sync(0xffffffffu, valid && !(dc2 > reach * reach * 1.000002f))) continue;
+            n32 += valid ? 1u : 0u;
             float e;
             const float q = tri_q(s_rec[jj * 4], s_rec[jj * 4 + 1], s_rec[jj * 4 + 2], s_rec[jj * 4 + 3], px, py, pz, e);
             const float qlo = q - e;
@@ -492,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
               s_lq[st.cnt * kThreads + tid] = qlo;
               st.cnt++;
             }
-            st.ub = fminf(st.ub, q + e);
+            if (q + e < st.ub) { st.ub = q + e; st.sub = __fsqrt_ru(st.ub); }
           }
           const float um = warp_max(valid ? st.ub : 0.f);
           const float su = sqrtf(um) + Rw;
@@ -517,18 +550,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_sdf_tiles(const SdfArgs A) {
     A.grid32[o] = (float)d;
     A.nearest[o] = st.best_id;
   }
-  unsigned long long a32 = n32, a64 = st.n64, ac = ncull;
+  unsigned long long a32 = n32, a64 = st.n64, ac = ncull, as = nsph;
   for (int o = 16; o > 0; o >>= 1) {
     a32 += __shfl_xor_sync(0xffffffffu, a32, o);
     a64 += __shfl_xor_sync(0xffffffffu, a64, o);
     ac += __shfl_xor_sync(0xffffffffu, ac, o);
+    as += __shfl_xor_sync(0xffffffffu, as, o);
   }
-  if (lane == 0) { atomicAdd(&s_stats[0], a32); atomicAdd(&s_stats[1], a64); atomicAdd(&s_stats[2], ac); }
+  if (lane == 0) { atomicAdd(&s_stats[0], a32); atomicAdd(&s_stats[1], a64); atomicAdd(&s_stats[2], ac); atomicAdd(&s_stats[3], as); }
   __syncthreads();
   if (tid < 3) atomicAdd(&A.stats[tid], s_stats[tid]);
+  if (tid == 3) atomicAdd(&A.stats[4], s_stats[3]);
 }
 
-constexpr size_t kSdfSmem = (size_t)kCap * 64 + (size_t)kCap * 4 + (size_t)kListCap * kThreads * 8 + (size_t)kMaxRanges * 12;
+constexpr size_t kSdfSmem = (size_t)kCap * 64 + (size_t)kCap * 16 + (size_t)kCap * 4 + (size_t)kListCap * kThreads * 8 + (size_t)kMaxRanges * 12;
 
 int run_build(Template& T, cudaStream_t s) {
   const int N = T.N, nF = T.nF, nV = T.nV;
@@ -538,16 +573,16 @@ int run_build(Template& T, cudaStream_t s) {
 
   int *cell_count = nullptr, *cell_start = nullptr, *tri_cell = nullptr, *tri_id = nullptr;
   unsigned *cell_bb = nullptr, *max_ext = nullptr;
-  float4* rec32 = nullptr;
+  float4 *rec32 = nullptr, *sph = nullptr;
   double* rec64 = nullptr;
   // one scratch allocation, stream ordered
   const size_t b_count = 2 * ncell * sizeof(int);          // count + fill
   const size_t b_start = (ncell + 1) * sizeof(int);
   const size_t b_bb = 6 * ncell * sizeof(unsigned);
   const size_t b_tri = 2 * (size_t)nF * sizeof(int);       // tri_cell + tri_id
-  const size_t b_r32 = (size_t)nF * 64, b_r64 = (size_t)nF * 72;
+  const size_t b_r32 = (size_t)nF * 64, b_r64 = (size_t)nF * 72, b_sph = (size_t)nF * 16;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t total = al(b_count) + al(b_start) + al(b_bb) + al(b_tri) + al(b_r32) + al(b_r64) + 256;
+  const size_t total = al(b_count) + al(b_start) + al(b_bb) + al(b_tri) + al(b_r32) + al(b_r64) + al(b_sph) + 256;
   unsigned char* scratch = nullptr;
   MO_CUDA(cudaMallocAsync(&scratch, total, s));
   unsigned char* p = scratch;
@@ -557,6 +592,7 @@ int run_build(Template& T, cudaStream_t s) {
   tri_cell = (int*)p; tri_id = tri_cell + nF; p += al(b_tri);
   rec32 = (float4*)p; p += al(b_r32);
   rec64 = (double*)p; p += al(b_r64);
+  sph = (float4*)p; p += al(b_sph);
   max_ext = (unsigned*)p;
   int* cell_fill = cell_count + ncell;
 
@@ -564,13 +600,13 @@ int run_build(Template& T, cudaStream_t s) {
   k_init_cells<<<div_up((long long)ncell, 256), 256, 0, s>>>(cell_bb, (int)ncell);
   MO_LAUNCH_CHECK();
   MO_CUDA(cudaMemsetAsync(max_ext, 0, sizeof(unsigned), s));
-  MO_CUDA(cudaMemsetAsync(T.d_stats, 0, 4 * sizeof(unsigned long long), s));
+  MO_CUDA(cudaMemsetAsync(T.d_stats, 0, 8 * sizeof(unsigned long long), s));
 
   k_tri_count<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, nV, N, nc, cell_count, cell_bb, tri_cell, max_ext, T.d_stats);
   MO_LAUNCH_CHECK();
   k_scan<<<1, 1024, 0, s>>>(cell_count, cell_start, (int)ncell);
   MO_LAUNCH_CHECK();
-  k_tri_fill<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, tri_cell, cell_start, cell_fill, rec32, rec64, tri_id);
+  k_tri_fill<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, tri_cell, cell_start, cell_fill, rec32, sph, rec64, tri_id);
   MO_LAUNCH_CHECK();
 
   if (T.z0 > 0 || T.z1 < N) {
@@ -580,11 +616,12 @@ int run_build(Template& T, cudaStream_t s) {
 
   SdfArgs A;
   A.N = N; A.nc = nc; A.ntile = ntile; A.z0 = T.z0; A.z1 = T.z1;
-  A.tz0 = T.z0 / kTile;
-  const int tz1 = (T.z1 - 1) / kTile;
+  A.ntz = div_up(N, kTileZ);
+  A.tz0 = T.z0 / kTileZ;
+  const int tz1 = (T.z1 - 1) / kTileZ;
   A.cs = (float)((double)kCellVox / N);
   A.max_ext = max_ext; A.cell_start = cell_start; A.cell_bb = cell_bb;
-  A.rec32 = rec32; A.rec64 = rec64; A.tri_id = tri_id;
+  A.rec32 = rec32; A.sph = sph; A.rec64 = rec64; A.tri_id = tri_id;
   A.grid64 = T.d_grid64; A.grid32 = T.d_grid32; A.nearest = T.d_nearest; A.stats = T.d_stats;
   static bool attr_set[64] = {};
   if (!attr_set[T.device & 63]) {
