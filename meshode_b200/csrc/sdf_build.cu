@@ -4,20 +4,27 @@
 //
 // Pipeline (all on the caller's stream, no host synchronisation):
 //   k_bbox / k_xform / k_vnorm   FP64 normalisation, bit-identical to the CPU arithmetic
-//   k_tri_count / k_scan / k_tri_fill
-//                                triangles binned by centroid into cells of 4^3 voxels;
-//                                per-cell tight AABB; records written cell-sorted
-//   k_sdf_tiles                  one CTA per 8^3-voxel tile, one lane per voxel:
-//                                cells are swept ring by ring around the tile, culled
-//                                against the tile's running upper bound; surviving
-//                                triangle records are staged in shared memory; each warp
-//                                (4x4x2 voxels) culls staged candidates against its own
-//                                bound (lanes over candidates, warp-shuffle max / ballot)
-//                                and runs the dense branch-free FP32 point-triangle test
-//                                on the survivors (lanes over voxels, record broadcast from
-//                                shared memory).  Candidates whose FP32 lower bound is
-//                                within the rigorous error band of the running minimum are
-//                                queued per lane and re-evaluated exactly in FP64
+//   k_tri_count / k_cell_alloc / k_tri_fill / k_cluster
+//                                triangles binned by centroid into cells of 4^3 voxels; the
+//                                triangles of a cell form a CLUSTER with a bounding cylinder
+//                                (centre, mean normal, half height tau, radius rho): for a
+//                                smooth surface a flat pill box.  Every triangle carries the
+//                                same bound (a disc).  Cells are grouped 4x4x4 into coarse
+//                                cells (16^3 voxels) with an AABB.
+//   k_sdf_tiles                  one CTA per 8x8x4-voxel tile, one lane per voxel, one warp per
+//                                4x4x2 block.  Coarse cells are swept ring by ring around the
+//                                tile; clusters of the surviving coarse cells are tested
+//                                against the tile (CTA), then against the block (lanes over
+//                                clusters), then against every voxel (lanes over voxels); the
+//                                triangles of a surviving cluster are staged in the warp's
+//                                shared memory, pre-tested per voxel with their disc bound and
+//                                only then evaluated with the branch-free FP32 point-triangle
+//                                test.  The cylinder bound removes the tangential slack of a
+//                                bounding-sphere test: a triangle seen face-on from distance d
+//                                is a candidate only for the voxels above it, not for every
+//                                voxel within sqrt(2 d rho) of them.  Candidates whose FP32
+//                                lower bound is within the rigorous error band of the running
+//                                minimum are queued per lane and re-evaluated exactly in FP64
 //                                (Ericson's closest point, the oracle's arithmetic), so the
 //                                stored distance and nearest index are the FP64 result.
 #include <cfloat>
@@ -28,14 +35,17 @@ namespace mo {
 namespace {
 
 constexpr int kTile = 8;          // voxels per tile edge in x and y
-constexpr int kTileZ = 4;         // voxels per tile in z: 8 warps per CTA, two CTAs per SM hide each other's barriers
-constexpr int kCellVox = 4;       // voxels per bin-cell edge
+constexpr int kTileZ = 4;         // voxels per tile in z
+constexpr int kCellVox = 4;       // voxels per cluster-cell edge
+constexpr int kCoarse = 4;        // cluster cells per coarse-cell edge
 constexpr int kWarps = kTile * kTile * kTileZ / 32;
 constexpr int kThreads = kWarps * 32;
-constexpr int kCtasPerSm = 2;
-constexpr int kCap = 768;         // triangle records staged per chunk (64 B record + 16 B bounding sphere each)
-constexpr int kMaxRanges = 1024;  // cell ranges collected per pass
-constexpr int kListCap = 12;      // per-lane queue of FP64 candidates
+constexpr int kCtasPerSm = 3;
+constexpr int kCoarseChunk = 32;                              // coarse cells expanded per pass
+constexpr int kListMax = kCoarseChunk * kCoarse * kCoarse * kCoarse;   // clusters listed per pass
+constexpr int kMaxCoarse = 1024;  // coarse cells collected per enumeration chunk
+constexpr int kQueueCap = 8;      // per-lane queue of FP64 candidates
+constexpr int kRecParts = 6;      // float4 per triangle record: 4 for the distance test, 2 for the disc bound
 
 // |q_fp32 - q_exact| <= kA * |p-a|^2 + kB for coordinates inside the unit cube: record
 // rounding moves the triangle by <= 3e-8 (=> 1.1e-7*sqrt(pp) <= 5e-6*pp + 5e-10), the
@@ -44,13 +54,15 @@ constexpr float kErrA = 1.2e-5f;
 constexpr float kErrB = 1.2e-9f;
 
 struct SdfArgs {
-  int N, nc, ntile, ntz, tz0, z0, z1;
-  float cs;                       // cell size in normalised units
+  int N, nc, ncc, ntile, tz0, z0, z1;
+  float ccs;                      // coarse cell size in normalised units
   const unsigned* max_ext;        // bit pattern of the largest triangle AABB extent
-  const int* cell_start;          // [ncell+1]
-  const unsigned* cell_bb;        // [ncell*6] ordered-uint lo xyz, hi xyz
-  const float4* rec32;            // [nF*4] cell-sorted FP32 records
-  const float4* sph;              // [nF] cell-sorted bounding spheres (centre, radius rounded up)
+  const int* coarse_cnt;          // [ncoarse] triangles binned into the coarse cell
+  const unsigned* coarse_bb;      // [ncoarse*6] ordered-uint lo xyz, hi xyz of those triangles
+  const int2* cl_sc;              // [ncell] (first record, count) of the cell's triangles
+  const float4* cl_c;             // [ncell] cluster centre, cylinder radius
+  const float4* cl_n;             // [ncell] cluster axis (unit), cylinder half height
+  const float4* rec;              // [nF*6] cell-sorted FP32 records (4 distance + 2 disc)
   const double* rec64;            // [nF*9] cell-sorted FP64 vertices
   const int* tri_id;              // [nF] cell-sorted -> original triangle index
   double* grid64;
@@ -111,25 +123,29 @@ __global__ void k_fill_grid(double* g64, float* g32, int* nearest, size_t n) {
   if (i >= n) return;
   g64[i] = 1e30; g32[i] = 1e30f; nearest[i] = -1;   // uniformgrid.cc:9-17
 }
-
 // ---------------------------------------------------------------------------------
-// binning
+// binning and clusters
 // ---------------------------------------------------------------------------------
-__global__ void k_init_cells(unsigned* __restrict__ cell_bb, int ncell) {
+__global__ void k_init_coarse(unsigned* __restrict__ coarse_bb, int ncoarse) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncell) return;
+  if (c >= ncoarse) return;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) { cell_bb[6 * (size_t)c + j] = 0xffffffffu; cell_bb[6 * (size_t)c + 3 + j] = 0u; }
+  for (int j = 0; j < 3; ++j) { coarse_bb[6 * (size_t)c + j] = 0xffffffffu; coarse_bb[6 * (size_t)c + 3 + j] = 0u; }
 }
 
 __device__ __forceinline__ int cell_coord(double x, int N, int nc) {
   const double c = floor(x * (double)N * (1.0 / kCellVox));
   return c < 0.0 ? 0 : (c > (double)(nc - 1) ? nc - 1 : (int)c);
 }
+// cells of one coarse cell are contiguous: index = coarse * 64 + local
+__device__ __forceinline__ int cell_index(int cx, int cy, int cz, int ncc) {
+  const int C = ((cz >> 2) * ncc + (cy >> 2)) * ncc + (cx >> 2);
+  return C * 64 + (((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3));
+}
 
-__global__ void k_tri_count(const double* __restrict__ Vn, const int* __restrict__ F, int nF, int nV, int N, int nc,
-                            int* __restrict__ cell_count, unsigned* __restrict__ cell_bb, int* __restrict__ tri_cell,
-                            unsigned* __restrict__ max_ext, unsigned long long* __restrict__ stats) {
+__global__ void k_tri_count(const double* __restrict__ Vn, const int* __restrict__ F, int nF, int nV, int N, int nc, int ncc,
+                            int* __restrict__ cell_count, int* __restrict__ coarse_cnt, unsigned* __restrict__ coarse_bb,
+                            int* __restrict__ tri_cell, unsigned* __restrict__ max_ext, unsigned long long* __restrict__ stats) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nF) return;
   const int i0 = F[3 * (size_t)t], i1 = F[3 * (size_t)t + 1], i2 = F[3 * (size_t)t + 2];
@@ -145,53 +161,61 @@ __global__ void k_tri_count(const double* __restrict__ Vn, const int* __restrict
     finite = finite && isfinite(a) && isfinite(b) && isfinite(c);
   }
   if (!finite) { tri_cell[t] = -1; atomicOr(&stats[3], 2ull); return; }
-  const int cx = cell_coord(ce[0], N, nc), cy = cell_coord(ce[1], N, nc), cz = cell_coord(ce[2], N, nc);
-  const int c = (cz * nc + cy) * nc + cx;
+  const int c = cell_index(cell_coord(ce[0], N, nc), cell_coord(ce[1], N, nc), cell_coord(ce[2], N, nc), ncc);
+  const int C = c >> 6;
   float ext = 0.f;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const float l = __double2float_rd(lo[j]), h = __double2float_ru(hi[j]);
-    atomicMin(&cell_bb[6 * (size_t)c + j], f2o(l));
-    atomicMax(&cell_bb[6 * (size_t)c + 3 + j], f2o(h));
+    atomicMin(&coarse_bb[6 * (size_t)C + j], f2o(l));
+    atomicMax(&coarse_bb[6 * (size_t)C + 3 + j], f2o(h));
     ext = fmaxf(ext, __fsub_ru(h, l));
   }
   atomicMax(max_ext, __float_as_uint(ext));
   atomicAdd(&cell_count[c], 1);
+  atomicAdd(&coarse_cnt[C], 1);
   tri_cell[t] = c;
 }
 
-// exclusive scan of n ints by one CTA of 1024 threads
-__global__ void k_scan(const int* __restrict__ in, int* __restrict__ out, int n) {
-  __shared__ int s_warp[32];
-  const int tid = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int b = tid * per, e = min(n, b + per);
-  int sum = 0;
-  for (int i = b; i < e; ++i) sum += in[i];
-  int incl = sum;
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
-  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-  __syncthreads();
-  if (tid < 32) {
-    int w = s_warp[tid];
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) w += v; }
-    s_warp[tid] = w;
-  }
-  __syncthreads();
-  int run = incl - sum + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
-  for (int i = b; i < e; ++i) { out[i] = run; run += in[i]; }
-  if (tid == 1023) out[n] = s_warp[31];
+// hands every cell a private range of the record arrays.  The order of the ranges is irrelevant
+// (a cluster record holds its own start and count), so one warp-aggregated atomic per 32 cells
+// replaces a prefix sum over the cell grid.
+__global__ void k_cell_alloc(const int* __restrict__ cell_count, int ncell, int* __restrict__ total, int2* __restrict__ cl_sc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int cnt = c < ncell ? cell_count[c] : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const int sum = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && sum > 0) base = atomicAdd(total, sum);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (c < ncell) cl_sc[c] = make_int2(base + incl - cnt, cnt);
 }
 
+// bounding cylinder of the points v[0..n) about centre cf with (float) axis nf: half height and radius,
+// rounded up and padded for the FP32 evaluation in cyl_skip (see there)
+__device__ __forceinline__ void cyl_extent(const double* v, const float cf[3], const float nf[3], double& max_h, double& max_t2) {
+  const double nl = sqrt((double)nf[0] * nf[0] + (double)nf[1] * nf[1] + (double)nf[2] * nf[2]);
+  const double d[3] = {v[0] - (double)cf[0], v[1] - (double)cf[1], v[2] - (double)cf[2]};
+  const double h = (d[0] * nf[0] + d[1] * nf[1] + d[2] * nf[2]) / nl;
+  const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  max_h = fmax(max_h, fabs(h));
+  max_t2 = fmax(max_t2, dd - h * h);
+}
+__device__ __forceinline__ float pad_tau(double max_h) { return __double2float_ru(max_h * 1.000001 + 4e-7); }
+__device__ __forceinline__ float pad_rho(double max_t2) { return __double2float_ru(sqrt(fmax(max_t2, 0.0)) * 1.000001 + 2e-7); }
+
 __global__ void k_tri_fill(const double* __restrict__ Vn, const int* __restrict__ F, int nF,
-                           const int* __restrict__ tri_cell, const int* __restrict__ cell_start,
-                           int* __restrict__ cell_fill, float4* __restrict__ rec32, float4* __restrict__ sph,
+                           const int* __restrict__ tri_cell, const int2* __restrict__ cl_sc,
+                           int* __restrict__ cell_fill, float4* __restrict__ rec,
                            double* __restrict__ rec64, int* __restrict__ tri_id) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nF) return;
   const int c = tri_cell[t];
   if (c < 0) return;
-  const int slot = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+  const int slot = cl_sc[c].x + atomicAdd(&cell_fill[c], 1);
   const int i0 = F[3 * (size_t)t], i1 = F[3 * (size_t)t + 1], i2 = F[3 * (size_t)t + 2];
   double a[3], b[3], cc[3], ab[3], ac[3];
 #pragma unroll
@@ -220,28 +244,113 @@ __global__ void k_tri_fill(const double* __restrict__ Vn, const int* __restrict_
   const float i11 = e11 > 0.0 ? (float)(1.0 / e11) : 0.f;
   const float i22 = e22 > 0.0 ? (float)(1.0 / e22) : 0.f;
   const float ibc = bc2 > 0.0 ? (float)(1.0 / bc2) : 0.f;
-  rec32[4 * (size_t)slot + 0] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)e11);
-  rec32[4 * (size_t)slot + 1] = make_float4((float)ab[0], (float)ab[1], (float)ab[2], (float)e12);
-  rec32[4 * (size_t)slot + 2] = make_float4((float)ac[0], (float)ac[1], (float)ac[2], (float)e22);
-  rec32[4 * (size_t)slot + 3] = make_float4(r3x, isinf(i11) ? 0.f : i11, isinf(i22) ? 0.f : i22, isinf(ibc) ? 0.f : ibc);
-  // bounding sphere about the centroid; the radius absorbs the float rounding of the centre
+  float4* r = rec + kRecParts * (size_t)slot;
+  r[0] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)e11);
+  r[1] = make_float4((float)ab[0], (float)ab[1], (float)ab[2], (float)e12);
+  r[2] = make_float4((float)ac[0], (float)ac[1], (float)ac[2], (float)e22);
+  r[3] = make_float4(r3x, isinf(i11) ? 0.f : i11, isinf(i22) ? 0.f : i22, isinf(ibc) ? 0.f : ibc);
+  // disc bound: centroid, unit normal, half height (rounding only) and radius
   {
-    double cx[3], r2 = 0.0;
-    float cf[3];
+    double n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+    const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    float cf[3], nf[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { cx[j] = (a[j] + b[j] + cc[j]) * (1.0 / 3.0); cf[j] = (float)cx[j]; }
-    const double* vs[3] = {a, b, cc};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double d2 = 0.0;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) { const double d = vs[k][j] - (double)cf[j]; d2 += d * d; }
-      r2 = fmax(r2, d2);
+    for (int j = 0; j < 3; ++j) {
+      cf[j] = (float)((a[j] + b[j] + cc[j]) * (1.0 / 3.0));
+      nf[j] = len > 1e-200 ? (float)(n[j] / len) : (j == 2 ? 1.f : 0.f);
     }
-    // + 2e-7: float rounding of the query point (<= 5.2e-8) and of the centre, with margin
-    sph[slot] = make_float4(cf[0], cf[1], cf[2], __double2float_ru(sqrt(r2) * 1.000001 + 2e-7));
+    if (!(fabsf(nf[0]) + fabsf(nf[1]) + fabsf(nf[2]) > 0.5f)) { nf[0] = 0.f; nf[1] = 0.f; nf[2] = 1.f; }
+    double mh = 0.0, mt2 = 0.0;
+    cyl_extent(a, cf, nf, mh, mt2); cyl_extent(b, cf, nf, mh, mt2); cyl_extent(cc, cf, nf, mh, mt2);
+    r[4] = make_float4(cf[0], cf[1], cf[2], pad_rho(mt2));
+    r[5] = make_float4(nf[0], nf[1], nf[2], pad_tau(mh));
   }
   tri_id[slot] = t;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// one warp per cell: bounding cylinder of the cell's triangles about their mean centroid, axis = area-weighted
+// mean normal (any axis gives a valid bound; this one makes it flat for a smooth patch)
+__global__ void k_cluster(const int2* __restrict__ cl_sc, int ncell, const double* __restrict__ rec64,
+                          float4* __restrict__ cl_c, float4* __restrict__ cl_n) {
+  const int cell = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  const int2 sc = cl_sc[cell];
+  if (sc.y == 0) return;
+  double sn[3] = {0.0, 0.0, 0.0}, sm[3] = {0.0, 0.0, 0.0};
+  for (int i = lane; i < sc.y; i += 32) {
+    const double* tv = rec64 + 9 * (size_t)(sc.x + i);
+    double ab[3], ac[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { ab[j] = tv[3 + j] - tv[j]; ac[j] = tv[6 + j] - tv[j]; sm[j] += (tv[j] + tv[3 + j] + tv[6 + j]) * (1.0 / 3.0); }
+    sn[0] += ab[1] * ac[2] - ab[2] * ac[1]; sn[1] += ab[2] * ac[0] - ab[0] * ac[2]; sn[2] += ab[0] * ac[1] - ab[1] * ac[0];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { sn[j] = warp_sum_d(sn[j]); sm[j] = warp_sum_d(sm[j]); }
+  const double len = sqrt(sn[0] * sn[0] + sn[1] * sn[1] + sn[2] * sn[2]);
+  float cf[3], nf[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    cf[j] = (float)(sm[j] / (double)sc.y);
+    nf[j] = len > 1e-200 ? (float)(sn[j] / len) : (j == 2 ? 1.f : 0.f);
+  }
+  if (!(fabsf(nf[0]) + fabsf(nf[1]) + fabsf(nf[2]) > 0.5f)) { nf[0] = 0.f; nf[1] = 0.f; nf[2] = 1.f; }
+  double mh = 0.0, mt2 = 0.0;
+  for (int i = lane; i < sc.y; i += 32) {
+    const double* tv = rec64 + 9 * (size_t)(sc.x + i);
+    cyl_extent(tv, cf, nf, mh, mt2); cyl_extent(tv + 3, cf, nf, mh, mt2); cyl_extent(tv + 6, cf, nf, mh, mt2);
+  }
+  mh = warp_max_d(mh); mt2 = warp_max_d(mt2);
+  if (lane == 0) {
+    cl_c[cell] = make_float4(cf[0], cf[1], cf[2], pad_rho(mt2));
+    cl_n[cell] = make_float4(nf[0], nf[1], nf[2], pad_tau(mh));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Cylinder bound.  A cluster (or a single triangle) lies inside the cylinder
+//   { x : |(x-c).n| <= tau,  |(x-c) - ((x-c).n) n| <= rho }      (n unit, c = C.xyz, rho = C.w, tau = Nm.w)
+// so dist(p, cluster)^2 >= max(|h|-tau, 0)^2 + max(t-rho, 0)^2 with h = (p-c).n, t^2 = |p-c|^2 - h^2.
+// cyl_skip returns true only if that lower bound exceeds ub, evaluated in FP32 without a square
+// root and with every rounding on the safe side for coordinates inside the unit cube:
+//   |h_fp32 - h| <= 4e-7 |p-c| <= 4e-7 (|p-c|^2 + 1/4)     (subtraction, dot product, |n_fp32| = 1 +- 2e-7)
+//   t^2 >= t2_fp32 - (1.6e-6 |p-c|^2 + 1e-7)
+// tau and rho are stored rounded up and padded (pad_tau: +4e-7 covers the 1e-7 above and the
+// rounding of the query point to FP32; pad_rho: +2e-7).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool cyl_skip(const float px, const float py, const float pz, const float ub, const float4 C,
+                                         const float4 Nm) {
+  const float dx = px - C.x, dy = py - C.y, dz = pz - C.z;
+  const float dc2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float h = fmaf(dz, Nm.z, fmaf(dy, Nm.y, dx * Nm.x));
+  const float ah = fmaxf(fabsf(h) - fmaf(4e-7f, dc2, Nm.w), 0.f);
+  const float A = fmaf(-0.999999f * ah, ah, ub);                        // ub - (axial gap)^2
+  const float t2 = fmaf(-h, h, dc2) - fmaf(1.6e-6f, dc2, 1e-7f);        // lower bound of the squared radial distance
+  const float r2 = C.w * C.w;
+  const float S = t2 + r2;
+  const float B = (S - A) - 4e-7f * (S + fabsf(A));                     // t2 + rho^2 - A, rounded down
+  // radial gap^2 > A  <=>  t > rho and t2 + rho^2 - A > 2 rho t
+  const bool radial = (t2 > r2) && (B > 0.f) && (B * B * 0.99999f > 4.f * r2 * t2);
+  return (A < 0.f) || radial;
+}
+// the same bound as a number (ordering only, not rigorous)
+__device__ __forceinline__ float cyl_lb2(const float px, const float py, const float pz, const float4 C, const float4 Nm) {
+  const float dx = px - C.x, dy = py - C.y, dz = pz - C.z;
+  const float dc2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float h = fmaf(dz, Nm.z, fmaf(dy, Nm.y, dx * Nm.x));
+  const float ah = fmaxf(fabsf(h) - Nm.w, 0.f);
+  const float tg = fmaxf(sqrtf(fmaxf(fmaf(-h, h, dc2), 0.f)) - C.w, 0.f);
+  return fmaf(ah, ah, tg * tg);
 }
 
 // ---------------------------------------------------------------------------------
@@ -361,12 +470,10 @@ __device__ __noinline__ double tri_exact64(const double* __restrict__ tv, const 
   const double dx = dsub(p[0], q[0]), dy = dsub(p[1], q[1]), dz = dsub(p[2], q[2]);
   return dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
 }
-
 struct LaneState {
   double best64;   // exact minimum so far
   int best_id;     // its original triangle index (lowest on exact ties)
   float ub;        // rigorous FP32 upper bound of the exact minimum
-  float sub;       // upper bound of sqrt(ub) (for the bounding-sphere pre-test)
   int cnt;         // queued FP64 candidates
   unsigned n64;
 };
@@ -384,7 +491,6 @@ __device__ __forceinline__ void flush_queue(LaneState& st, const int* s_lid, con
   }
   st.cnt = 0;
   if (st.best_id >= 0) st.ub = fminf(st.ub, __double2float_ru(st.best64));
-  st.sub = __fsqrt_ru(st.ub);
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -393,164 +499,224 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// per-lane view of the kernel state that the cluster routine needs
+struct WarpCtx {
+  float4* s_tri;      // this warp's staging buffer [kRecParts][32]
+  const int* s_lid;
+  float* s_lq;
+  int* s_lidw;
+  int tid, lane;
+  bool valid;
+  float px, py, pz;
+  double pxd, pyd, pzd;
+};
+
+// One cluster against the warp's 32 voxels: per-voxel cylinder test, then the cluster's triangles are staged
+// 32 at a time in the warp's shared memory, pre-tested per voxel with their disc bound and evaluated in FP32
+// only if some lane still needs them.
+__device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx& w, LaneState& st, const float4 C,
+                                                const float4 Nm, const int2 sc, unsigned& n_cyl, unsigned& n_disc,
+                                                unsigned& n32) {
+  const bool act = w.valid && !cyl_skip(w.px, w.py, w.pz, st.ub, C, Nm);
+  n_cyl += w.valid ? 1u : 0u;
+  if (!__any_sync(0xffffffffu, act)) return;
+  for (int tb = 0; tb < sc.y; tb += 32) {
+    const int nt = min(32, sc.y - tb);
+    __syncwarp();
+    if (w.lane < nt) {
+      const float4* r = A.rec + kRecParts * (size_t)(sc.x + tb + w.lane);
+#pragma unroll
+      for (int part = 0; part < kRecParts; ++part) w.s_tri[part * 32 + w.lane] = __ldg(r + part);
+    }
+    __syncwarp();
+    n_disc += w.valid ? (unsigned)nt : 0u;
+    for (int j = 0; j < nt; ++j) {
+      const bool need = act && !cyl_skip(w.px, w.py, w.pz, st.ub, w.s_tri[4 * 32 + j], w.s_tri[5 * 32 + j]);
+      if (!__any_sync(0xffffffffu, need)) continue;
+      n32 += w.valid ? 1u : 0u;
+      float e;
+      const float q = tri_q(w.s_tri[j], w.s_tri[32 + j], w.s_tri[64 + j], w.s_tri[96 + j], w.px, w.py, w.pz, e);
+      const float qlo = q - e;
+      if (w.valid && qlo <= st.ub) {
+        if (st.cnt == kQueueCap) flush_queue(st, w.s_lid, w.s_lq, w.tid, A, w.pxd, w.pyd, w.pzd);
+        w.s_lidw[st.cnt * kThreads + w.tid] = sc.x + tb + j;
+        w.s_lq[st.cnt * kThreads + w.tid] = qlo;
+        st.cnt++;
+      }
+      st.ub = fminf(st.ub, q + e);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* s_rec = reinterpret_cast<float4*>(smem_raw);                 // kCap*4
-  float4* s_sph = s_rec + kCap * 4;                                    // kCap
-  int* s_gidx = reinterpret_cast<int*>(s_sph + kCap);                  // kCap
-  int* s_lid = s_gidx + kCap;                                          // kListCap*kThreads
-  float* s_lq = reinterpret_cast<float*>(s_lid + kListCap * kThreads); // kListCap*kThreads
-  int* s_rstart = reinterpret_cast<int*>(s_lq + kListCap * kThreads);  // kMaxRanges
-  int* s_rcnt = s_rstart + kMaxRanges;
-  int* s_roff = s_rcnt + kMaxRanges;
-  __shared__ int s_nr, s_total;
+  float4* s_tri = reinterpret_cast<float4*>(smem_raw);                   // [kWarps][kRecParts][32]
+  float4* s_wc = s_tri + kWarps * kRecParts * 32;                        // [kWarps][32] block survivors: centre, rho
+  float4* s_wn = s_wc + kWarps * 32;                                     // [kWarps][32] axis, tau
+  int2* s_wsc = reinterpret_cast<int2*>(s_wn + kWarps * 32);             // [kWarps][32] start, count
+  int* s_lid = reinterpret_cast<int*>(s_wsc + kWarps * 32);              // [kQueueCap][kThreads]
+  float* s_lq = reinterpret_cast<float*>(s_lid + kQueueCap * kThreads);  // [kQueueCap][kThreads]
+  int* s_list = reinterpret_cast<int*>(s_lq + kQueueCap * kThreads);     // [kListMax]
+  int* s_coarse = s_list + kListMax;                                     // [kMaxCoarse]
+  __shared__ int s_ncoarse, s_nlist;
   __shared__ unsigned s_ub[2];
-  __shared__ unsigned long long s_stats[4];
+  __shared__ unsigned long long s_stats[5];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = A.N, nc = A.nc;
+  const int N = A.N, ncc = A.ncc;
   const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile, tz = A.tz0 + blockIdx.x / (A.ntile * A.ntile);   // tz in units of kTileZ
 
   // this lane's voxel; the warp owns a 4x4x2 block of the tile
   const int bx = tx * kTile + (warp & 1) * 4, by = ty * kTile + ((warp >> 1) & 1) * 4, bz = tz * kTileZ + (warp >> 2) * 2;
   const int vx = bx + (lane & 3), vy = by + ((lane >> 2) & 3), vz = bz + (lane >> 4);
-  const bool valid = vx < N && vy < N && vz < N && vz >= A.z0 && vz < A.z1;
   const double invN = 1.0 / (double)N;
-  const double pxd = __ddiv_rn((double)vx, (double)N), pyd = __ddiv_rn((double)vy, (double)N),
-               pzd = __ddiv_rn((double)vz, (double)N);   // mesh.cc:115-117
-  const float px = (float)pxd, py = (float)pyd, pz = (float)pzd;
+  WarpCtx w;
+  w.s_tri = s_tri + warp * kRecParts * 32; w.s_lid = s_lid; w.s_lidw = s_lid; w.s_lq = s_lq; w.tid = tid; w.lane = lane;
+  w.valid = vx < N && vy < N && vz < N && vz >= A.z0 && vz < A.z1;
+  w.pxd = __ddiv_rn((double)vx, (double)N); w.pyd = __ddiv_rn((double)vy, (double)N);
+  w.pzd = __ddiv_rn((double)vz, (double)N);   // mesh.cc:115-117
+  w.px = (float)w.pxd; w.py = (float)w.pyd; w.pz = (float)w.pzd;
+  const bool valid = w.valid;
+  // block and tile bounding spheres (sample points, unclipped)
   const float wcx = (float)((bx + 1.5) * invN), wcy = (float)((by + 1.5) * invN), wcz = (float)((bz + 0.5) * invN);
   const float Rw = (float)(2.1795 * invN * 1.0001);   // half diagonal of the 3x3x1-interval sample box
-
-  // tile sample box (clipped to the grid and the slab)
+  const float tcx = (float)((tx * kTile + 3.5) * invN), tcy = (float)((ty * kTile + 3.5) * invN), tcz = (float)((tz * kTileZ + 1.5) * invN);
+  const float Rt = (float)(5.1721 * invN * 1.0001);   // half diagonal of the 7x7x3-interval sample box
+  // tile sample box (clipped to the grid and the slab) for the coarse AABB test
   const float tlo[3] = {(float)(tx * kTile * invN), (float)(ty * kTile * invN), (float)(max(tz * kTileZ, A.z0) * invN)};
   const float thi[3] = {(float)(min(tx * kTile + kTile - 1, N - 1) * invN), (float)(min(ty * kTile + kTile - 1, N - 1) * invN),
                         (float)(min(min(tz * kTileZ + kTileZ - 1, N - 1), A.z1 - 1) * invN)};
 
+  const float kInf = __int_as_float(0x7f800000);
   LaneState st;
-  st.best64 = DBL_MAX; st.best_id = -1; st.ub = __int_as_float(0x7f800000); st.sub = st.ub; st.cnt = 0; st.n64 = 0;
-  unsigned n32 = 0, ncull = 0, nsph = 0;
-  float thr_w = __int_as_float(0x7f800000);
-  float ub_cta = __int_as_float(0x7f800000);
+  st.best64 = DBL_MAX; st.best_id = -1; st.ub = kInf; st.cnt = 0; st.n64 = 0;
+  unsigned n32 = 0, n_cyl = 0, n_disc = 0;
+  float thr_w = kInf;     // (sqrt(max ub of the block) + Rw)^2
+  float ub_cta = kInf;    // max ub of the tile
+  float thr_t = kInf;     // (sqrt(ub_cta) + Rt)^2
   const float max_ext = __uint_as_float(*A.max_ext);
-  if (tid < 4) s_stats[tid] = 0ull;
+  if (tid < 5) s_stats[tid] = 0ull;
   if (tid < 2) s_ub[tid] = 0u;
   int par = 0;
 
-  constexpr int kCz = kTileZ / kCellVox;                // cells per tile in z
-  const int cbx = 2 * tx, cby = 2 * ty, cbz = kCz * tz;   // the tile's 2 x 2 x kCz cell block
-  for (int r = 0; r <= nc; ++r) {
+  const int Cx = tx >> 1, Cy = ty >> 1, Cz = tz >> 2;   // the tile's coarse cell (a tile is 2 x 2 x 1 cells)
+  for (int r = 0; r <= ncc; ++r) {
     if (r >= 1) {
-      const float lb = (float)(r - 1) * A.cs - max_ext;   // nothing binned in ring >= r is closer than this
+      const float lb = (float)(r - 1) * A.ccs - max_ext;   // nothing binned in ring >= r is closer than this
       if (lb > 0.f && lb * lb * 0.9999f > ub_cta) break;
+      const int q = r - 1;                                 // ring r-1 already enclosed the whole coarse grid
+      if (Cx - q <= 0 && Cy - q <= 0 && Cz - q <= 0 && Cx + q >= ncc - 1 && Cy + q >= ncc - 1 && Cz + q >= ncc - 1) break;
     }
-    if (r >= 1) {   // ring r-1 already enclosed the whole cell grid
-      const int q = r - 1;
-      if (cbx - q <= 0 && cby - q <= 0 && cbz - q <= 0 && cbx + 1 + q >= nc - 1 && cby + 1 + q >= nc - 1 &&
-          cbz + kCz - 1 + q >= nc - 1)
-        break;
-    }
-    const int side = 2 + 2 * r, sidez = kCz + 2 * r;
-    const int x0 = cbx - r, y0 = cby - r, z0c = cbz - r;
-    const int nenum = side * side * sidez;
-    for (int base = 0; base < nenum; base += kMaxRanges) {
+    const int side = 1 + 2 * r;
+    const int x0 = Cx - r, y0 = Cy - r, z0c = Cz - r;
+    const int nenum = side * side * side;
+    for (int base = 0; base < nenum; base += kMaxCoarse) {
       __syncthreads();
-      if (tid == 0) { s_nr = 0; s_total = 0; }
+      if (tid == 0) s_ncoarse = 0;
       __syncthreads();
-      const int lim = min(nenum, base + kMaxRanges);
+      const int lim = min(nenum, base + kMaxCoarse);
       for (int i = base + tid; i < lim; i += kThreads) {
         const int ix = i % side, iy = (i / side) % side, iz = i / (side * side);
-        if (r > 0 && ix > 0 && ix < side - 1 && iy > 0 && iy < side - 1 && iz > 0 && iz < sidez - 1) continue;
+        if (r > 0 && ix > 0 && ix < side - 1 && iy > 0 && iy < side - 1 && iz > 0 && iz < side - 1) continue;
         const int cx = x0 + ix, cy = y0 + iy, cz = z0c + iz;
-        if ((unsigned)cx >= (unsigned)nc || (unsigned)cy >= (unsigned)nc || (unsigned)cz >= (unsigned)nc) continue;
-        const int c = (cz * nc + cy) * nc + cx;
-        const int cs0 = A.cell_start[c], cnt = A.cell_start[c + 1] - cs0;
-        if (cnt == 0) continue;
+        if ((unsigned)cx >= (unsigned)ncc || (unsigned)cy >= (unsigned)ncc || (unsigned)cz >= (unsigned)ncc) continue;
+        const int c = (cz * ncc + cy) * ncc + cx;
+        if (A.coarse_cnt[c] == 0) continue;
         float d2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const float lo = o2f(A.cell_bb[6 * (size_t)c + j]), hi = o2f(A.cell_bb[6 * (size_t)c + 3 + j]);
+          const float lo = o2f(A.coarse_bb[6 * (size_t)c + j]), hi = o2f(A.coarse_bb[6 * (size_t)c + 3 + j]);
           const float gap = fmaxf(0.f, fmaxf(lo - thi[j], tlo[j] - hi));
           d2 = fmaf(gap, gap, d2);
         }
-        if (d2 * 0.9999f <= ub_cta) {
-          const int slot = atomicAdd(&s_nr, 1);
-          s_rstart[slot] = cs0; s_rcnt[slot] = cnt; s_roff[slot] = atomicAdd(&s_total, cnt);
-        }
+        if (d2 * 0.9999f <= ub_cta) s_coarse[atomicAdd(&s_ncoarse, 1)] = c;
       }
       __syncthreads();
-      const int nr = s_nr, total = s_total;
-      for (int cb = 0; cb < total; cb += kCap) {
-        // ---- stage up to kCap candidate records in shared memory -------------------
-        for (int ri = warp; ri < nr; ri += kWarps) {
-          const int off = s_roff[ri], cnt = s_rcnt[ri], start = s_rstart[ri];
-          const int lo = max(off, cb), hi = min(off + cnt, cb + kCap);
-          for (int q4 = lane; q4 < (hi - lo) * 4; q4 += 32) {
-            const int rec = lo + (q4 >> 2), part = q4 & 3;
-            const int g = start + (rec - off);
-            s_rec[(rec - cb) * 4 + part] = __ldg(&A.rec32[4 * (size_t)g + part]);
-            if (part == 0) s_gidx[rec - cb] = g;
-            if (part == 1) s_sph[rec - cb] = __ldg(&A.sph[g]);
-          }
+      const int ncoarse = s_ncoarse;
+      for (int cb = 0; cb < ncoarse; cb += kCoarseChunk) {
+        // ---- clusters of up to kCoarseChunk coarse cells against the tile -------------------------
+        if (tid == 0) s_nlist = 0;
+        __syncthreads();
+        const int nexp = min(kCoarseChunk, ncoarse - cb) * 64;
+        for (int i = tid; i < nexp; i += kThreads) {
+          const int cell = s_coarse[cb + (i >> 6)] * 64 + (i & 63);
+          if (__ldg(&A.cl_sc[cell]).y == 0) continue;
+          n_cyl++;
+          if (!cyl_skip(tcx, tcy, tcz, thr_t, __ldg(&A.cl_c[cell]), __ldg(&A.cl_n[cell]))) s_list[atomicAdd(&s_nlist, 1)] = cell;
         }
         __syncthreads();
-        const int nrec = min(kCap, total - cb);
-        // ---- per warp: cull against the warp bound, dense test on the survivors ------
-        for (int b = 0; b < nrec; b += 32) {
-          const int j = b + lane;
-          const bool has = j < nrec;
-          const int jr = has ? j : 0;
-          float ec;
-          const float qc = tri_q(s_rec[jr * 4], s_rec[jr * 4 + 1], s_rec[jr * 4 + 2], s_rec[jr * 4 + 3], wcx, wcy, wcz, ec);
-          unsigned m = __ballot_sync(0xffffffffu, has && (qc - ec <= thr_w));
-          ncull += has ? 1u : 0u;
-          nsph += valid ? (unsigned)__popc(m) : 0u;
-          while (m) {
-            const int jj = b + __ffs(m) - 1;
-            m &= m - 1;
-            // per-voxel pre-test against the triangle's bounding sphere: |p - c| - rho is a lower bound of
-            // the distance; if it exceeds every lane's upper bound the exact test is skipped for the warp
-            const float4 sp = s_sph[jj];
-            const float dx = px - sp.x, dy = py - sp.y, dz = pz - sp.z;
-            const float dc2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const float reach = st.sub + sp.w;
-            if (!__any_sync(0xffffffffu, valid && !(dc2 > reach * reach * 1.000002f))) continue;
-            n32 += valid ? 1u : 0u;
-            float e;
-            const float q = tri_q(s_rec[jj * 4], s_rec[jj * 4 + 1], s_rec[jj * 4 + 2], s_rec[jj * 4 + 3], px, py, pz, e);
-            const float qlo = q - e;
-            if (valid && qlo <= st.ub) {
-              if (st.cnt == kListCap) flush_queue(st, s_lid, s_lq, tid, A, pxd, pyd, pzd);
-              s_lid[st.cnt * kThreads + tid] = s_gidx[jj];
-              s_lq[st.cnt * kThreads + tid] = qlo;
-              st.cnt++;
+        const int n = s_nlist;
+        if (n > 0) {
+          // ---- pass 1 (block without a bound yet): the cluster nearest to the block goes first ------
+          int first = -1;
+          if (thr_w == kInf) {
+            float bl = kInf;
+            for (int b = 0; b < n; b += 32) {
+              const int j = b + lane;
+              if (j < n) {
+                const int cell = s_list[j];
+                const float l = cyl_lb2(wcx, wcy, wcz, __ldg(&A.cl_c[cell]), __ldg(&A.cl_n[cell]));
+                if (l < bl) { bl = l; first = cell; }
+              }
             }
-            if (q + e < st.ub) { st.ub = q + e; st.sub = __fsqrt_ru(st.ub); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+              const int oc = __shfl_xor_sync(0xffffffffu, first, o);
+              if (ol < bl || (ol == bl && oc > first)) { bl = ol; first = oc; }
+            }
+            n_cyl += (unsigned)((n + 31) >> 5);
+            if (first >= 0) {
+              process_cluster(A, w, st, __ldg(&A.cl_c[first]), __ldg(&A.cl_n[first]), __ldg(&A.cl_sc[first]), n_cyl, n_disc, n32);
+              const float su = sqrtf(warp_max(valid ? st.ub : 0.f)) + Rw;
+              thr_w = su * su * 1.00001f;
+            }
           }
-          const float um = warp_max(valid ? st.ub : 0.f);
-          const float su = sqrtf(um) + Rw;
-          thr_w = su * su * 1.00001f;
+          // ---- pass 2: lanes over clusters against the block, survivors against every voxel ---------
+          for (int b = 0; b < n; b += 32) {
+            const int j = b + lane;
+            const bool has = j < n;
+            const int cell = s_list[has ? j : 0];
+            const float4 C = __ldg(&A.cl_c[cell]), Nm = __ldg(&A.cl_n[cell]);
+            const bool keep = has && cell != first && !cyl_skip(wcx, wcy, wcz, thr_w, C, Nm);
+            n_cyl += has ? 1u : 0u;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m == 0u) continue;
+            __syncwarp();
+            if (keep) {
+              const int pos = __popc(m & ((1u << lane) - 1u));
+              s_wc[warp * 32 + pos] = C; s_wn[warp * 32 + pos] = Nm; s_wsc[warp * 32 + pos] = __ldg(&A.cl_sc[cell]);
+            }
+            __syncwarp();
+            const int np = __popc(m);
+            for (int k = 0; k < np; ++k)
+              process_cluster(A, w, st, s_wc[warp * 32 + k], s_wn[warp * 32 + k], s_wsc[warp * 32 + k], n_cyl, n_disc, n32);
+            const float su = sqrtf(warp_max(valid ? st.ub : 0.f)) + Rw;
+            thr_w = su * su * 1.00001f;
+          }
         }
         const float um = warp_max(valid ? st.ub : 0.f);
         if (lane == 0) atomicMax(&s_ub[par], __float_as_uint(um));
         __syncthreads();
         ub_cta = __uint_as_float(s_ub[par]);
         par ^= 1;
-        if (tid == 0) s_ub[par] = 0u;   // next chunk's slot; not touched again before two more barriers
+        if (tid == 0) s_ub[par] = 0u;   // next pass's slot; not touched again before two more barriers
+        const float st_ = sqrtf(ub_cta) + Rt;
+        thr_t = st_ * st_ * 1.00001f;
       }
     }
   }
 
   // ---- exact FP64 evaluation of everything still queued, then store ------------------
   if (valid) {
-    flush_queue(st, s_lid, s_lq, tid, A, pxd, pyd, pzd);
+    flush_queue(st, s_lid, s_lq, tid, A, w.pxd, w.pyd, w.pzd);
     const size_t o = ((size_t)vz * N + vy) * N + vx;
     const double d = st.best_id >= 0 ? __dsqrt_rn(st.best64) : 1e30;   // mesh.cc:146
     A.grid64[o] = d;
     A.grid32[o] = (float)d;
     A.nearest[o] = st.best_id;
   }
-  unsigned long long a32 = n32, a64 = st.n64, ac = ncull, as = nsph;
+  unsigned long long a32 = n32, a64 = st.n64, ac = n_cyl, as = n_disc;
   for (int o = 16; o > 0; o >>= 1) {
     a32 += __shfl_xor_sync(0xffffffffu, a32, o);
     a64 += __shfl_xor_sync(0xffffffffu, a64, o);
@@ -563,50 +729,53 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
   if (tid == 3) atomicAdd(&A.stats[4], s_stats[3]);
 }
 
-constexpr size_t kSdfSmem = (size_t)kCap * 64 + (size_t)kCap * 16 + (size_t)kCap * 4 + (size_t)kListCap * kThreads * 8 + (size_t)kMaxRanges * 12;
+constexpr size_t kSdfSmem = (size_t)kWarps * kRecParts * 32 * 16 + (size_t)kWarps * 32 * (16 + 16 + 8) +
+                            (size_t)kQueueCap * kThreads * 8 + (size_t)kListMax * 4 + (size_t)kMaxCoarse * 4;
 
 int run_build(Template& T, cudaStream_t s) {
   const int N = T.N, nF = T.nF, nV = T.nV;
-  const int ntile = div_up(N, kTile), nc = 2 * ntile;
-  const size_t ncell = (size_t)nc * nc * nc;
+  const int ntile = div_up(N, kTile), nc = 2 * ntile, ncc = div_up(nc, kCoarse);
+  const size_t ncoarse = (size_t)ncc * ncc * ncc, ncell = ncoarse * 64;
   const size_t nvox = (size_t)N * N * N;
 
-  int *cell_count = nullptr, *cell_start = nullptr, *tri_cell = nullptr, *tri_id = nullptr;
-  unsigned *cell_bb = nullptr, *max_ext = nullptr;
-  float4 *rec32 = nullptr, *sph = nullptr;
-  double* rec64 = nullptr;
   // one scratch allocation, stream ordered
-  const size_t b_count = 2 * ncell * sizeof(int);          // count + fill
-  const size_t b_start = (ncell + 1) * sizeof(int);
-  const size_t b_bb = 6 * ncell * sizeof(unsigned);
-  const size_t b_tri = 2 * (size_t)nF * sizeof(int);       // tri_cell + tri_id
-  const size_t b_r32 = (size_t)nF * 64, b_r64 = (size_t)nF * 72, b_sph = (size_t)nF * 16;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t total = al(b_count) + al(b_start) + al(b_bb) + al(b_tri) + al(b_r32) + al(b_r64) + al(b_sph) + 256;
+  const size_t b_count = (2 * ncell + ncoarse) * sizeof(int);   // cell count + cell fill + coarse count (zeroed together)
+  const size_t b_sc = ncell * sizeof(int2);
+  const size_t b_cl = ncell * sizeof(float4);
+  const size_t b_bb = 6 * ncoarse * sizeof(unsigned);
+  const size_t b_tri = 2 * (size_t)nF * sizeof(int);            // tri_cell + tri_id
+  const size_t b_rec = (size_t)nF * kRecParts * 16, b_r64 = (size_t)nF * 72;
+  const size_t total = al(b_count) + al(b_sc) + 2 * al(b_cl) + al(b_bb) + al(b_tri) + al(b_rec) + al(b_r64) + 256;
   unsigned char* scratch = nullptr;
   MO_CUDA(cudaMallocAsync(&scratch, total, s));
   unsigned char* p = scratch;
-  cell_count = (int*)p; p += al(b_count);
-  cell_start = (int*)p; p += al(b_start);
-  cell_bb = (unsigned*)p; p += al(b_bb);
-  tri_cell = (int*)p; tri_id = tri_cell + nF; p += al(b_tri);
-  rec32 = (float4*)p; p += al(b_r32);
-  rec64 = (double*)p; p += al(b_r64);
-  sph = (float4*)p; p += al(b_sph);
-  max_ext = (unsigned*)p;
+  int* cell_count = (int*)p; p += al(b_count);
   int* cell_fill = cell_count + ncell;
+  int* coarse_cnt = cell_fill + ncell;
+  int2* cl_sc = (int2*)p; p += al(b_sc);
+  float4* cl_c = (float4*)p; p += al(b_cl);
+  float4* cl_n = (float4*)p; p += al(b_cl);
+  unsigned* coarse_bb = (unsigned*)p; p += al(b_bb);
+  int* tri_cell = (int*)p; int* tri_id = tri_cell + nF; p += al(b_tri);
+  float4* rec = (float4*)p; p += al(b_rec);
+  double* rec64 = (double*)p; p += al(b_r64);
+  unsigned* max_ext = (unsigned*)p;      // [0] largest triangle extent, [1] record counter
+  int* total_cnt = (int*)(max_ext + 1);
 
   MO_CUDA(cudaMemsetAsync(cell_count, 0, b_count, s));
-  k_init_cells<<<div_up((long long)ncell, 256), 256, 0, s>>>(cell_bb, (int)ncell);
-  MO_LAUNCH_CHECK();
-  MO_CUDA(cudaMemsetAsync(max_ext, 0, sizeof(unsigned), s));
+  MO_CUDA(cudaMemsetAsync(max_ext, 0, 2 * sizeof(unsigned), s));
   MO_CUDA(cudaMemsetAsync(T.d_stats, 0, 8 * sizeof(unsigned long long), s));
-
-  k_tri_count<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, nV, N, nc, cell_count, cell_bb, tri_cell, max_ext, T.d_stats);
+  k_init_coarse<<<div_up((long long)ncoarse, 256), 256, 0, s>>>(coarse_bb, (int)ncoarse);
   MO_LAUNCH_CHECK();
-  k_scan<<<1, 1024, 0, s>>>(cell_count, cell_start, (int)ncell);
+  k_tri_count<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, nV, N, nc, ncc, cell_count, coarse_cnt, coarse_bb, tri_cell,
+                                               max_ext, T.d_stats);
   MO_LAUNCH_CHECK();
-  k_tri_fill<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, tri_cell, cell_start, cell_fill, rec32, sph, rec64, tri_id);
+  k_cell_alloc<<<div_up((long long)ncell, 256), 256, 0, s>>>(cell_count, (int)ncell, total_cnt, cl_sc);
+  MO_LAUNCH_CHECK();
+  k_tri_fill<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, tri_cell, cl_sc, cell_fill, rec, rec64, tri_id);
+  MO_LAUNCH_CHECK();
+  k_cluster<<<div_up((long long)ncell * 32, 256), 256, 0, s>>>(cl_sc, (int)ncell, rec64, cl_c, cl_n);
   MO_LAUNCH_CHECK();
 
   if (T.z0 > 0 || T.z1 < N) {
@@ -615,13 +784,13 @@ int run_build(Template& T, cudaStream_t s) {
   }
 
   SdfArgs A;
-  A.N = N; A.nc = nc; A.ntile = ntile; A.z0 = T.z0; A.z1 = T.z1;
-  A.ntz = div_up(N, kTileZ);
+  A.N = N; A.nc = nc; A.ncc = ncc; A.ntile = ntile; A.z0 = T.z0; A.z1 = T.z1;
   A.tz0 = T.z0 / kTileZ;
   const int tz1 = (T.z1 - 1) / kTileZ;
-  A.cs = (float)((double)kCellVox / N);
-  A.max_ext = max_ext; A.cell_start = cell_start; A.cell_bb = cell_bb;
-  A.rec32 = rec32; A.sph = sph; A.rec64 = rec64; A.tri_id = tri_id;
+  A.ccs = (float)((double)(kCellVox * kCoarse) / N);
+  A.max_ext = max_ext; A.coarse_cnt = coarse_cnt; A.coarse_bb = coarse_bb;
+  A.cl_sc = cl_sc; A.cl_c = cl_c; A.cl_n = cl_n;
+  A.rec = rec; A.rec64 = rec64; A.tri_id = tri_id;
   A.grid64 = T.d_grid64; A.grid32 = T.d_grid32; A.nearest = T.d_nearest; A.stats = T.d_stats;
   static bool attr_set[64] = {};
   if (!attr_set[T.device & 63]) {
