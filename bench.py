@@ -307,18 +307,19 @@ def run_b200(a):
         alg = pair_iter_bytes(nV, nE) * a.iters * n
         ach = alg / (d_ms * 1e-3) / 1e9
         # DRAM traffic of this kernel per pair-iteration from the committed ncu --set full capture
-        # (profiles/r01_deform_v3.txt: 148 pairs x 200 iterations, dram read 15.28 GB + write 2.55 GB)
-        ncu_bytes_per_pair_iter = (15.279365e9 + 2.546122e9) / (148 * 200)
-        roof = {"kernel": "k_deform_adam (one launch per step and rank: %d pairs x %d iterations)" % (n, a.iters),
+        # (profiles/r01_deform_v5.txt: 148 pairs x 300 iterations, dram read 21.91 GB + write 3.52 GB)
+        ncu_bytes_per_pair_iter = (21.911742e9 + 3.515466e9) / (148 * 300)
+        roof = {"kernel": "k_deform_adam_fused (one launch per step and rank: %d pairs x %d iterations)" % (n, a.iters),
                 "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "traffic": ncu_bytes_per_pair_iter * n * a.iters,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu capture (148 pairs x 200 iterations, "
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu capture (148 pairs x 300 iterations, "
                                 "%.0f kB per pair-iteration) scaled to this launch" % (ncu_bytes_per_pair_iter / 1e3),
                 "peak_source": hbm_src + " (sustained: timed inside a seconds-long step)",
                 "launch_ms": d_ms, "share_of_step": d_ms / ms_step,
                 "note": "algorithmic bytes = (28*V + 20*E + 72*V) per pair-iteration (SURVEY s8d) = %.3f MB; the kernel "
-                        "keeps vertices, rest positions and gradient in shared memory, so HBM is not its limiter (ncu: "
-                        "the shared-memory/L1 data pipe is, l1tex__throughput 77%%) and the fraction can exceed 1" %
+                        "keeps vertices and rest positions in shared memory and the gradient in registers, so HBM is not its "
+                        "limiter (ncu: the shared-memory/L1 data pipe is, l1tex__throughput 80%%: 8.8 wavefronts per 128-bit "
+                        "neighbour gather) and the fraction can exceed 1" %
                         (pair_iter_bytes(nV, nE) / 1e6)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
