@@ -209,6 +209,22 @@ int mo_ceres_problem(int dist_param_id, int kind, const double* d_V, const doubl
                      const double* d_rest, int nE, double lambda, double* d_cost2, double* d_gV, double* d_gR,
                      mo_stream_t stream);
 
+/* ceres::Solve(options, &problem, &summary) for those problems with the options of the C++ drivers
+ * (src/lib/deformer.cc:55-74, :135-153: max_num_iterations = 100, everything else Ceres' defaults:
+ * trust-region Levenberg-Marquardt, initial radius 1e4, function / gradient / parameter tolerances
+ * 1e-6 / 1e-10 / 1e-8, Jacobi scaling).  d_V [nV,3] (and d_R [nV,3] for kind ROT) are optimised in
+ * place.  The LM step solves (J^T J + D^T D) delta = -g matrix-free with Jacobi-preconditioned CG
+ * (relative residual cg_tolerance, default 1e-10; at most max_cg_iterations, default 4000) where Ceres
+ * uses a sparse Cholesky factorisation.  h_summary (HOST, 10 doubles, may be NULL): initial cost,
+ * final cost, final distance cost ("Vertices cost"), final edge cost ("Rigidity cost"), LM iterations,
+ * accepted steps, total CG iterations, termination (0 function tolerance, 1 gradient tolerance, 2
+ * parameter tolerance, 3 iteration limit, 4 five invalid steps in a row, 5 radius underflow), final
+ * trust-region radius, final max |gradient|.  verbose != 0 prints Ceres-style progress lines.
+ * Synchronises the stream (the LM loop reads its scalars back). */
+int mo_ceres_solve(int dist_param_id, int kind, double* d_V, double* d_R, int nV, const int* d_I, const double* d_rest,
+                   int nE, double lambda, int max_iterations, int max_cg_iterations, double cg_tolerance, int verbose,
+                   double* h_summary, mo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mo_nearest_vertex": [_vp, _i, _vp, _i, _vp, _vp, _vp],
     "mo_ceres_edges": [_i, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp],
     "mo_ceres_problem": [_i, _i, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp],
+    "mo_ceres_solve": [_i, _i, _vp, _vp, _i, _vp, _vp, _i, _d, _i, _i, _d, _i, _vp, _vp],
 }
 _RESTYPES = {"mo_last_error": C.c_char_p, "mo_launch_count": C.c_ulonglong}
 

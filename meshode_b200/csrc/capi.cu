@@ -401,6 +401,23 @@ int mo_ceres_problem(int dist_param_id, int kind, const double* d_V, const doubl
   return ceres_problem(TD, kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, d_cost2, d_gV, d_gR, (cudaStream_t)stream);
 }
 
+int mo_ceres_solve(int dist_param_id, int kind, double* d_V, double* d_R, int nV, const int* d_I, const double* d_rest,
+                   int nE, double lambda, int max_iterations, int max_cg_iterations, double cg_tolerance, int verbose,
+                   double* h_summary, mo_stream_t stream) {
+  MO_REQUIRE(kind == MO_CERES_EDGE || kind == MO_CERES_ADAPTIVE_EDGE || kind == MO_CERES_ROT_EDGE, "unknown Ceres edge kind");
+  MO_REQUIRE(nV >= 0 && nE >= 0 && max_iterations >= 0, "negative size");
+  MO_REQUIRE(nV == 0 || d_V, "null vertex pointer");
+  MO_REQUIRE(nE == 0 || (d_I && d_rest), "null edge pointer");
+  MO_REQUIRE(kind != MO_CERES_ROT_EDGE || nV == 0 || d_R, "EdgeLossWithRot needs the rotation parameters");
+  Template* TD = nullptr;
+  if (dist_param_id >= 0) {
+    TD = lookup(dist_param_id);
+    if (!TD) return MO_ERR_BAD_HANDLE;
+  }
+  return ceres_solve(TD, kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, max_iterations, max_cg_iterations, cg_tolerance, verbose,
+                     h_summary, (cudaStream_t)stream);
+}
+
 int mo_normalize_by_template(float* d_V, int n, int param_id, int inverse, mo_stream_t stream) {
   Template* T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;

@@ -93,6 +93,8 @@ int ceres_edges(int kind, const double* d_V, const double* d_R, int nV, const in
                 double lambda, double* d_res, double* d_jac, cudaStream_t s);
 int ceres_problem(const Template* TD, int kind, const double* d_V, const double* d_R, int nV, const int* d_I,
                   const double* d_rest, int nE, double lambda, double* d_cost2, double* d_gV, double* d_gR, cudaStream_t s);
+int ceres_solve(const Template* TD, int kind, double* d_V, double* d_R, int nV, const int* d_I, const double* d_rest, int nE,
+                double lambda, int max_iters, int max_cg, double cg_tol, int verbose, double* h_summary, cudaStream_t s);
 
 // deform.cu
 int deform_batch_adam(Template* const* TD, Template* const* TE, float* const* h_V, int B, int iters, double lr,

@@ -315,3 +315,38 @@ def CeresProblem(dist_param_id, kind, V, R, I, rest, lam):
                                                _ptr(R), V.shape[0], _ptr(I), _ptr(rest), I.shape[0], float(lam),
                                                _ptr(cost), _ptr(gV), _ptr(gR), _stream(V)))
     return cost, gV, gR
+
+
+SOLVE_TERMINATION = ("function tolerance", "gradient tolerance", "parameter tolerance", "iteration limit",
+                     "invalid steps", "radius underflow")
+
+
+def CeresSolve(dist_param_id, kind, V, R, I, rest, lam, max_iterations=100, max_cg_iterations=4000, cg_tolerance=1e-10,
+               verbose=False):
+    """ceres::Solve for the Deformer problems (src/lib/deformer.cc:55-74, :135-153): Levenberg-Marquardt with
+    Ceres' default options, the LM step solved matrix-free with preconditioned CG on the GPU.  ``V`` [n,3]
+    (and ``R`` [n,3] for capi.CERES_ROT_EDGE) float64 CUDA tensors are optimised IN PLACE; returns a summary
+    dict (initial_cost, final_cost, vertices_cost, rigidity_cost, iterations, accepted, cg_iterations,
+    termination)."""
+    import ctypes as C
+    _check(V, torch.float64, 3, "V")
+    if not V.is_cuda:
+        raise ValueError("CeresSolve optimises in place: V must be a CUDA tensor")
+    dev = V.device
+    rot = kind == capi.CERES_ROT_EDGE
+    if rot:
+        _check(R, torch.float64, 3, "R")
+        if not R.is_cuda:
+            raise ValueError("CeresSolve optimises in place: R must be a CUDA tensor")
+    _check(I, torch.int32, 2, "I")
+    I = I.to(dev)
+    rest = _f64(rest, 3, "rest", dev)
+    summ = (C.c_double * 10)()
+    with torch.cuda.device(dev):
+        capi.check(capi.lib().mo_ceres_solve(_pid(dist_param_id) if dist_param_id is not None else -1, int(kind), _ptr(V),
+                                             _ptr(R) if rot else 0, V.shape[0], _ptr(I), _ptr(rest), I.shape[0], float(lam),
+                                             int(max_iterations), int(max_cg_iterations), float(cg_tolerance),
+                                             int(bool(verbose)), C.addressof(summ), _stream(V)))
+    return {"initial_cost": summ[0], "final_cost": summ[1], "vertices_cost": summ[2], "rigidity_cost": summ[3],
+            "iterations": int(summ[4]), "accepted": int(summ[5]), "cg_iterations": int(summ[6]),
+            "termination": SOLVE_TERMINATION[int(summ[7])], "radius": summ[8], "gradient_max": summ[9]}
