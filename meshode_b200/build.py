@@ -50,5 +50,27 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+APPS = ["rigid_deform", "rigid_rot_deform"]
+BIN = os.path.join(HERE, "bin")
+
+
+def build_apps(force=False):
+    """The re-hosted C++ drivers (apps/*.cc, reference src/app/*.cc) linked against the C-ABI library."""
+    build_lib()
+    os.makedirs(BIN, exist_ok=True)
+    appdir = os.path.join(HERE, "..", "apps")
+    deps = [os.path.join(appdir, f) for f in os.listdir(appdir) if f.endswith(".h")] + [LIB]
+    out = []
+    for a in APPS:
+        exe = os.path.join(BIN, a)
+        src = os.path.join(appdir, a + ".cc")
+        if force or _newer(exe, [src] + deps):
+            subprocess.check_call([_nvcc(), "-O2", "-std=c++17", "-x", "cu", *NVCC_FLAGS[:2], src, "-o", exe, "-L" + HERE,
+                                   "-lmeshode_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/.."])
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
+    print(build_apps(force="--force" in sys.argv))

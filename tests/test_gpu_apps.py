@@ -1,0 +1,101 @@
+"""The re-hosted C++ drivers (apps/, reference src/app/rigid_deform.cc and rigid_rot_deform.cc) end to end on
+the GPU: OBJ in, OBJ out, same console lines as the reference binaries."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_obj(path, V, F):
+    with open(path, "w") as fh:
+        for v in V:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(float(x) for x in v))
+        for f in F:
+            fh.write("f %d/%d/%d %d %d//%d\n" % (f[0] + 1, f[0] + 1, f[0] + 1, f[1] + 1, f[2] + 1, f[2] + 1))
+
+
+def _read_obj(path):
+    V, F = [], []
+    for ln in open(path):
+        t = ln.split()
+        if t and t[0] == "v":
+            V.append([float(x) for x in t[1:4]])
+        elif t and t[0] == "f":
+            F.append([int(x.split("/")[0]) - 1 for x in t[1:4]])
+    return np.array(V), np.array(F)
+
+
+def _exe(name):
+    from meshode_b200 import build
+    exes = dict(zip(build.APPS, build.build_apps()))
+    return exes[name]
+
+
+def _run(name, args):
+    p = subprocess.run([_exe(name)] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def _costs(out):
+    m = {k: float(re.search(k + r": ([-+0-9.eE]+)", out).group(1)) for k in ("Vertices cost", "Rigidity cost", "Final cost")}
+    first = float(re.search(r"^\s*0\s+([-+0-9.eE]+)", out, re.M).group(1))
+    return m, first
+
+
+@pytest.mark.parametrize("name,kind_name", [("rigid_deform", "EDGE"), ("rigid_rot_deform", "ROT_EDGE")])
+def test_driver_matches_the_library_path(tmp_path, oracle, pd, name, kind_name):
+    from meshode_b200 import capi
+    from meshode_b200.synth import synth_pair
+    srcV, srcF, tarV, tarF = synth_pair(11, 300, 500)
+    s_obj, t_obj, o_obj = (str(tmp_path / x) for x in ("s.obj", "t.obj", "o.obj"))
+    _write_obj(s_obj, srcV, srcF); _write_obj(t_obj, tarV, tarF)
+    lam = 0.7
+    out = _run(name, [s_obj, t_obj, o_obj, 32, 5000, lam])
+    assert "Source:\t\tNum vertices: 300\tNum faces: 596" in out and "Deformed" in out
+    costs, first = _costs(out)
+    assert costs["Final cost"] < first
+    oV, oF = _read_obj(o_obj)
+    assert np.array_equal(oF, srcF)
+    # the same problem through the Python binding, built the way the driver builds it (FP64 from the OBJ text)
+    tv = tarV.astype(np.float64)
+    mn, mx = tv.min(0), tv.max(0)
+    scale = (mx - mn).max() * 1.1; pos = mn - 0.05 * scale
+    tm = oracle.Template(tarV, tarF, 32)                      # float32 -> FP64 normalisation: the same numbers
+    assert abs(tm.scale - scale) <= 1e-15 * scale
+    V0 = (srcV.astype(np.float64) - pos) / scale
+    a = srcF.reshape(-1); b = np.roll(srcF, -1, axis=1).reshape(-1)
+    I = np.stack([a, b], 1).astype(np.int32); rest = V0[a] - V0[b]
+    pid = pd.InitializeDeformTemplate(torch.from_numpy(tarV).cuda(), torch.from_numpy(tarF).cuda(), 0, 32)
+    V = torch.from_numpy(V0.copy()).cuda(); R = torch.zeros_like(V)
+    kind = getattr(capi, "CERES_" + kind_name)
+    s = pd.CeresSolve(pid, kind, V, R if kind_name == "ROT_EDGE" else None, torch.from_numpy(I).cuda(),
+                      torch.from_numpy(rest).cuda(), lam)
+    assert abs(s["final_cost"] - costs["Final cost"]) <= 2e-5 * s["final_cost"]      # 6 significant digits on the console
+    want = V.cpu().numpy() * scale + pos                                              # Mesh::WriteOBJ denormalises
+    assert np.abs(oV - want).max() <= 2e-5 * np.abs(want).max()
+    pd.DestroyTemplate(pid)
+
+
+def test_rigid_deform_cfg1(tmp_path, meshes):
+    """cfg1 of BASELINE.json: rigid_deform data/source.obj -> data/target.obj, GRID_RESOLUTION=64, lambda=1."""
+    s_obj, t_obj, o_obj = (str(tmp_path / x) for x in ("source.obj", "target.obj", "out.obj"))
+    _write_obj(s_obj, meshes["srcV"], meshes["srcF"]); _write_obj(t_obj, meshes["tarV"], meshes["tarF"])
+    out = _run("rigid_deform", [s_obj, t_obj, o_obj, 64, 5000, 1])
+    print(out[-1500:])
+    costs, first = _costs(out)
+    assert costs["Final cost"] < 0.5 * first
+    oV, oF = _read_obj(o_obj)
+    assert oV.shape == meshes["srcV"].shape and np.array_equal(oF, meshes["srcF"]) and np.isfinite(oV).all()
+
+
+def test_usage_without_arguments():
+    p = subprocess.run([_exe("rigid_rot_deform")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and "rigid_rot_deform source.obj reference.obj output.obj" in p.stdout
