@@ -37,7 +37,7 @@ def pair_iter_bytes(nV, nE):
 
 
 FLOP_PER_TEST = 74  # canonical Ericson face-region path
-FLOP_PER_SPHERE_TEST = 12  # bounding-sphere pre-test: 3 sub, 3 fma/mul, reach^2 (add, 2 mul), compare
+FLOP_PER_BOUND_TEST = 38  # bounding-cylinder / disc test (sdf_build.cu cyl_skip): 3 sub, two 3-term dot products, axial and radial gaps, compares
 
 
 def parse():
@@ -356,20 +356,21 @@ def run_b200(a):
             stats = capi.template_build_stats(pid)
             pd.DestroyTemplate(pid)
         ms = float(np.mean(times))
-        tests = stats["fp32_tests"] + stats["cull_tests"]
-        flop = tests * FLOP_PER_TEST + stats["sphere_tests"] * FLOP_PER_SPHERE_TEST
+        flop = stats["fp32_tests"] * FLOP_PER_TEST + (stats["cull_tests"] + stats["disc_tests"]) * FLOP_PER_BOUND_TEST
         tf = flop / (ms * 1e-3) / 1e12
         line["sdf_build_128"] = {
             "metric": "grid-SDF build ms at 128^3", "value": ms, "unit": "ms", "target_triangles": int(F.shape[0]),
-            "fp32_tests": stats["fp32_tests"], "cull_tests": stats["cull_tests"], "sphere_tests": stats["sphere_tests"],
+            "fp32_tests": stats["fp32_tests"], "cluster_tests": stats["cull_tests"], "disc_tests": stats["disc_tests"],
             "fp64_tests": stats["fp64_tests"],
             "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": tf / fp32_tf,
                          "traffic": None,
                          "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 "
                                         "entry); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-                         "note": "achieved = ((dense + cull point-triangle tests executed) x 74 + sphere pre-tests x 12 FLOP, counted "
-                                 "by the kernel) / build time including binning; brute-force-equivalent N^3*M*74 = %.3g FLOP" %
-                                 (128 ** 3 * F.shape[0] * 74.0)}}
+                         "note": "achieved = (point-triangle tests executed x 74 + bounding-cylinder tests of clusters and "
+                                 "bounding-disc pre-tests of triangles x 38 FLOP, all counted by the kernel) / build time "
+                                 "including binning; the build is fast because it avoids the brute-force tests (N^3*M*74 = "
+                                 "%.3g FLOP), not because it saturates the FMA pipe: ncu issue slots 62%% busy, FMA pipe 26%%, "
+                                 "ALU 26%%, FP64 9%% (profiles/r01_sdf128_v4.txt)" % (128 ** 3 * F.shape[0] * 74.0)}}
         line["fp32_tflops_measured"] = fp32_tf
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------

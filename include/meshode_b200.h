@@ -98,12 +98,13 @@ int mo_template_copy_grid(int param_id, int direction, int z0, int z1, double* d
 int mo_template_vertices(int param_id, const double** d_Vn);
 
 /* Build statistics of the last grid build of this template (for roofline accounting):
- * point-triangle tests executed in FP32, exact FP64 re-evaluations, candidate-cull tests (a
- * point-triangle test against a block centre each) and bounding-sphere pre-tests (12 FLOP each).
+ * point-triangle tests executed in FP32 (74 FLOP each), exact FP64 re-evaluations, bounding-
+ * cylinder tests of triangle clusters against a tile, a block or a voxel, and bounding-disc pre-tests of
+ * single triangles against a voxel (both the same ~38 FLOP test, sdf_build.cu cyl_skip).
  * Synchronises `stream`.  Any out pointer may be NULL. */
 int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long* fp32_tests,
                             unsigned long long* fp64_tests, unsigned long long* cull_tests,
-                            unsigned long long* sphere_tests);
+                            unsigned long long* disc_tests);
 
 /* ---- NormalizeByTemplate / DenormalizeByTemplate (src/interface/normalize.cc:5-45) ---- */
 /* in place on float32 [n,3]; inverse = 0: (v - trans)/scale, inverse = 1: v*scale + trans,

@@ -141,4 +141,4 @@ def template_vertices(pid):
 def template_build_stats(pid, stream=0):
     a, b, c, d = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
     check(lib().mo_template_build_stats(int(pid), stream, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-    return {"fp32_tests": a.value, "fp64_tests": b.value, "cull_tests": c.value, "sphere_tests": d.value}
+    return {"fp32_tests": a.value, "fp64_tests": b.value, "cull_tests": c.value, "disc_tests": d.value}

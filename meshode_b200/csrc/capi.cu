@@ -220,7 +220,7 @@ int mo_template_vertices(int param_id, const double** d_Vn) {
 }
 
 int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long* fp32_tests, unsigned long long* fp64_tests,
-                            unsigned long long* cull_tests, unsigned long long* sphere_tests) {
+                            unsigned long long* cull_tests, unsigned long long* disc_tests) {
   Template* T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   unsigned long long h[8];
@@ -229,7 +229,7 @@ int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long
   if (fp32_tests) *fp32_tests = h[0];
   if (fp64_tests) *fp64_tests = h[1];
   if (cull_tests) *cull_tests = h[2];
-  if (sphere_tests) *sphere_tests = h[4];
+  if (disc_tests) *disc_tests = h[4];
   if (h[3]) {
     set_error("template holds invalid input: " + std::string((h[3] & 1) ? "[face index out of range] " : "") +
               ((h[3] & 2) ? "[non-finite vertex] " : "") + ((h[3] & 4) ? "[edge index out of range]" : ""));

@@ -27,6 +27,6 @@ for k in range(reps + 2):
     st = capi.template_build_stats(pid)
     pd.DestroyTemplate(pid)
 nvox = N ** 3
-print("N=%d tris=%d: %.3f ms (min %.3f) | per voxel: dense %.1f  sphere %.1f  cull %.1f  fp64 %.2f" %
-      (N, F.shape[0], np.mean(ts), np.min(ts), st["fp32_tests"] / nvox, st["sphere_tests"] / nvox, st["cull_tests"] / nvox,
+print("N=%d tris=%d: %.3f ms (min %.3f) | per voxel: dense %.1f  disc %.1f  cluster %.1f  fp64 %.2f" %
+      (N, F.shape[0], np.mean(ts), np.min(ts), st["fp32_tests"] / nvox, st["disc_tests"] / nvox, st["cull_tests"] / nvox,
        st["fp64_tests"] / nvox))
