@@ -99,3 +99,35 @@ def test_rigid_deform_cfg1(tmp_path, meshes):
 def test_usage_without_arguments():
     p = subprocess.run([_exe("rigid_rot_deform")], capture_output=True, text=True, timeout=60)
     assert p.returncode == 0 and "rigid_rot_deform source.obj reference.obj output.obj" in p.stdout
+
+
+def test_python_scripts_mirror_the_reference_cli(tmp_path):
+    """scripts/rigid_deform.py (reference src/python/rigid_deform.py: --source --target --output) with both engines,
+    and scripts/batch_deform.py on a two-line file list."""
+    import sys
+    from meshode_b200.synth import synth_pair
+    outs = {}
+    srcV, srcF, tarV, tarF = synth_pair(13, 400, 500)
+    s_obj, t_obj = str(tmp_path / "s.obj"), str(tmp_path / "t.obj")
+    _write_obj(s_obj, srcV, srcF); _write_obj(t_obj, tarV, tarF)
+    for eng in ("fused", "layers"):
+        o = str(tmp_path / ("o_%s.obj" % eng))
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "rigid_deform.py"), "--source", s_obj, "--target", t_obj,
+                            "--output", o, "--engine", eng, "--niter", "60", "--grid", "32"], capture_output=True, text=True,
+                           timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        if eng == "layers":
+            assert "iter=0 loss=" in p.stdout
+        outs[eng] = _read_obj(o)
+    assert np.array_equal(outs["fused"][1], srcF) and np.array_equal(outs["layers"][1], srcF)
+    # same loss, same optimiser: the two engines agree to the OBJ's six significant digits after 60 steps
+    assert np.abs(outs["fused"][0] - outs["layers"][0]).max() <= 2e-5 * np.abs(outs["fused"][0]).max()
+    assert np.abs(outs["fused"][0] - srcV).max() > 1e-3          # and the mesh did move
+    lst = tmp_path / "pairs.txt"
+    lst.write_text("%s %s %s\n%s %s %s\n" % (s_obj, t_obj, tmp_path / "b0.obj", t_obj, s_obj, tmp_path / "b1.obj"))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "batch_deform.py"), "--filelist", str(lst), "--niter", "60",
+                        "--grid", "32"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "2 pairs" in p.stdout, p.stderr[-2000:]
+    b0 = _read_obj(str(tmp_path / "b0.obj"))
+    assert np.array_equal(b0[0], outs["fused"][0])               # a pair deforms the same alone or in a batch
+    assert _read_obj(str(tmp_path / "b1.obj"))[0].shape == tarV.shape
