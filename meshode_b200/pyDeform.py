@@ -11,6 +11,7 @@ contiguity, shape and ``param_id`` are checked and violations raise.
 ``import torch`` must precede ``import pyDeform`` as in the reference (README.md:46-50) --
 here simply because this module imports torch itself.
 """
+import numpy as np
 import torch
 
 from . import capi
@@ -86,9 +87,23 @@ def LoadCadMesh(filename):
 
 
 def SolveLinear(tensorV, tensorF, tensorE, tensorRef, tensorGraphV, rigidity, with_rot):
-    raise NotImplementedError(
-        "SolveLinear is the sparse direct post-process (src/lib/linear.cc), outside the GPU hot path "
-        "(SURVEY.md s8f)")
+    """src/interface/linear_layer.cc:5-84: ``tensorV`` (float32 [n,3]) is overwritten with the least-squares
+    positions that follow the deformed graph ``tensorGraphV``.  Host code, as in the reference (the sparse
+    solve runs once per shape, after the optimisation).  With ``with_rot`` the reference reinterprets the
+    graph tensor as the per-vertex target positions (it must then have n rows)."""
+    from . import linear
+    V = tensorV.detach().cpu().numpy().astype(np.float64)
+    F = tensorF.detach().cpu().numpy()
+    GV = tensorGraphV.detach().cpu().numpy().astype(np.float64)
+    if not with_rot:
+        out = linear.linear_estimation(V, F, tensorE.detach().cpu().numpy(), tensorRef.detach().cpu().numpy().reshape(-1), GV,
+                                       float(rigidity))
+    else:
+        if GV.shape[0] != V.shape[0]:
+            raise ValueError("with_rot: tensorGraphV must hold one target position per vertex")
+        out = linear.linear_estimation_with_rot(V, F, GV, float(rigidity))
+    with torch.no_grad():
+        tensorV.copy_(torch.from_numpy(out.astype(np.float32)).to(tensorV.device))
 
 
 # ---- template ----------------------------------------------------------------------------
