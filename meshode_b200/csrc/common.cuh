@@ -32,6 +32,8 @@ struct Template {
   float* d_lambda = nullptr;    // [nEdges] (CAD only)
   int* d_csr_start = nullptr;   // [eV+1]
   int* d_csr_key = nullptr;     // [2*nEdges] 2*edge + side, ascending per vertex
+  float4* d_inc = nullptr;      // [2*nEdges] per-incidence records in CSR order: rest vector, other endpoint | side << 31 (built on first backward)
+  float* d_inc_lambda = nullptr;   // [2*nEdges] lambda per incidence (CAD only)
   float* d_v0 = nullptr;        // [eV,3] vertices at store time (rest = V0[v1] - V0[v0])
   float* d_cells = nullptr;     // [N^3][8] the eight corner values of every cell, one 32-byte record (deform engine; built on first use)
   unsigned* d_ell = nullptr;    // [ceil(ell_D/2)][eV] packed other endpoints per incident edge, built on first deform

@@ -148,34 +148,55 @@ __global__ void k_edges_forward(int kind, const float* __restrict__ V, int nV, c
   }
 }
 
-// one vertex's gradient: contributions in ascending (edge, side) order
-__device__ __forceinline__ void gather_vertex(const float* __restrict__ V, const int2* __restrict__ ev,
-                                              const float* __restrict__ rest, const float* __restrict__ lambda,
-                                              const int* __restrict__ keys, int kb, int ke, float acc[3],
-                                              double* edge_loss) {
+// Per-incidence records in CSR order: (rest vector of the edge, other endpoint | side << 31), 16 bytes.  The
+// backward pass of a vertex then streams its own contiguous records and gathers only V[other] (12 B) per
+// incidence, instead of key -> edge endpoints -> both vertices + rest vector (four dependent gathers).
+__global__ void k_csr_records(const int* __restrict__ keys, const int* __restrict__ start, int nV,
+                              const int2* __restrict__ ev, const float* __restrict__ rest,
+                              const float* __restrict__ lambda, float4* __restrict__ inc, float* __restrict__ inc_lambda) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= start[nV]) return;   // edges with an out-of-range endpoint own no keys
+  const int key = keys[i];
+  const int e = key >> 1, side = key & 1;
+  const int2 v = ev[e];
+  const unsigned other = (unsigned)(side ? v.x : v.y) | ((unsigned)side << 31);
+  inc[i] = make_float4(rest[3 * (size_t)e], rest[3 * (size_t)e + 1], rest[3 * (size_t)e + 2], __uint_as_float(other));
+  if (inc_lambda) inc_lambda[i] = lambda[e];
+}
+
+// one vertex's gradient from its records: the same operations in the same (ascending edge, side) order as
+// gather_vertex below, i.e. as the reference's serial scatter loop
+__device__ __forceinline__ void gather_vertex_rec(const float* __restrict__ V, const float self[3],
+                                                  const float4* __restrict__ inc, const float* __restrict__ inc_lambda,
+                                                  int kb, int ke, float acc[3], double* edge_loss) {
   for (int i = kb; i < ke; ++i) {
-    const int key = keys[i];
-    const int e = key >> 1, side = key & 1;
-    const int2 v = ev[e];
+    const float4 rec = __ldg(inc + i);
+    const unsigned ob = __float_as_uint(rec.w);
+    const int other = (int)(ob & 0x7fffffffu);
+    const bool side = (ob >> 31) != 0u;
     float lam2 = 1.f, lam = 1.f;
-    if (lambda) { lam = lambda[e]; lam2 = fmul(lam, lam); }   // cad_layer.cc:186-187
+    if (inc_lambda) { lam = __ldg(inc_lambda + i); lam2 = fmul(lam, lam); }   // cad_layer.cc:186-187
+    const float o[3] = {__ldg(V + 3 * (size_t)other), __ldg(V + 3 * (size_t)other + 1), __ldg(V + 3 * (size_t)other + 2)};
+    const float rs[3] = {rec.x, rec.y, rec.z};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      float r = fsub(fsub(__ldg(V + 3 * (size_t)v.y + k), __ldg(V + 3 * (size_t)v.x + k)), rest[3 * (size_t)e + k]);
-      if (edge_loss && side == 0) { const float l = lambda ? fmul(r, lam) : r; *edge_loss += (double)fmul(l, l); }
-      if (lambda) r = fmul(r, lam2);
+      // r = (V[v1] - V[v0]) - rest with (v0, v1) = (self, other) on side 0 and (other, self) on side 1
+      float r = fsub(side ? fsub(self[k], o[k]) : fsub(o[k], self[k]), rs[k]);
+      if (edge_loss && !side) { const float l = inc_lambda ? fmul(r, lam) : r; *edge_loss += (double)fmul(l, l); }
+      if (inc_lambda) r = fmul(r, lam2);
       acc[k] = side ? fadd(acc[k], r) : fsub(acc[k], r);        // rigid_layer.cc:123-128
     }
   }
 }
 
-__global__ void k_edges_backward_csr(const float* __restrict__ V, int nV, const int2* __restrict__ ev,
-                                     const float* __restrict__ rest, const float* __restrict__ lambda,
-                                     const int* __restrict__ start, const int* __restrict__ keys, float* __restrict__ grad) {
+__global__ void k_edges_backward_csr(const float* __restrict__ V, int nV, const float4* __restrict__ inc,
+                                     const float* __restrict__ inc_lambda, const int* __restrict__ start,
+                                     float* __restrict__ grad) {
   const int v = blockIdx.x * kBlock + threadIdx.x;
   if (v >= nV) return;
   float acc[3] = {0.f, 0.f, 0.f};
-  gather_vertex(V, ev, rest, lambda, keys, start[v], start[v + 1], acc, nullptr);
+  const float self[3] = {V[3 * (size_t)v], V[3 * (size_t)v + 1], V[3 * (size_t)v + 2]};
+  gather_vertex_rec(V, self, inc, inc_lambda, start[v], start[v + 1], acc, nullptr);
   grad[3 * (size_t)v] = acc[0]; grad[3 * (size_t)v + 1] = acc[1]; grad[3 * (size_t)v + 2] = acc[2];
 }
 
@@ -215,10 +236,10 @@ __global__ void k_edges_backward_atomic(int kind, const float* __restrict__ V, i
 
 // fused per-iteration loss: distance (Jet) + CSR edge gather + masked/weighted sum
 __global__ void __launch_bounds__(kBlock) k_loss_fused(const float* __restrict__ grid, int n, const float* __restrict__ V,
-                                                       int nV, const int2* __restrict__ ev, const float* __restrict__ rest,
-                                                       const float* __restrict__ lambda, const int* __restrict__ start,
-                                                       const int* __restrict__ keys, float w_edge, float mask_thr,
-                                                       double* __restrict__ loss, float* __restrict__ grad) {
+                                                       int nV, const float4* __restrict__ inc,
+                                                       const float* __restrict__ inc_lambda, const int* __restrict__ start,
+                                                       float w_edge, float mask_thr, double* __restrict__ loss,
+                                                       float* __restrict__ grad) {
   __shared__ double s_part[kBlock / 32];
   const int v = blockIdx.x * kBlock + threadIdx.x;
   double my = 0.0;
@@ -232,7 +253,8 @@ __global__ void __launch_bounds__(kBlock) k_loss_fused(const float* __restrict__
     if (mask_thr > 0.f && !(lossD < mask_thr)) gD[0] = gD[1] = gD[2] = 0.f;   // graph_loss_layer.py:18,40
     float gE[3] = {0.f, 0.f, 0.f};
     double le = 0.0;
-    if (start) gather_vertex(V, ev, rest, lambda, keys, start[v], start[v + 1], gE, loss ? &le : nullptr);
+    const float self[3] = {x, y, z};
+    if (start) gather_vertex_rec(V, self, inc, inc_lambda, start[v], start[v + 1], gE, loss ? &le : nullptr);
     my = (double)lossD + 0.5 * le * (double)w_edge;
     if (grad) {
 #pragma unroll
@@ -255,7 +277,8 @@ __global__ void __launch_bounds__(kBlock) k_loss_fused(const float* __restrict__
 
 void free_edges(Template& T, cudaStream_t s) {
   dev_free(T.d_ev, s); dev_free(T.d_rest, s); dev_free(T.d_lambda, s); dev_free(T.d_csr_start, s); dev_free(T.d_csr_key, s);
-  dev_free(T.d_v0, s); dev_free(T.d_ell, s); dev_free(T.d_nbr, s);
+  dev_free(T.d_v0, s); dev_free(T.d_ell, s); dev_free(T.d_nbr, s); dev_free(T.d_inc, s); dev_free(T.d_inc_lambda, s);
+  T.d_inc = nullptr; T.d_inc_lambda = nullptr;
   T.d_ev = nullptr; T.d_rest = nullptr; T.d_lambda = nullptr; T.d_csr_start = nullptr; T.d_csr_key = nullptr;
   T.d_v0 = nullptr; T.d_ell = nullptr; T.ell_D = 0; T.d_nbr = nullptr; T.nbr_W = 0;
   T.kind = MO_EDGES_NONE; T.nEdges = 0;
@@ -280,6 +303,8 @@ int edges_store(Template& T, int kind, const float* d_V, int nV, const int* d_F,
   }
   if (T.d_ell) { dev_free(T.d_ell, s); T.d_ell = nullptr; T.ell_D = 0; }
   if (T.d_nbr) { dev_free(T.d_nbr, s); T.d_nbr = nullptr; T.nbr_W = 0; }
+  if (T.d_inc) { dev_free(T.d_inc, s); T.d_inc = nullptr; }
+  if (T.d_inc_lambda) { dev_free(T.d_inc_lambda, s); T.d_inc_lambda = nullptr; }
   if (nV > 0) MO_CUDA(cudaMemcpyAsync(T.d_v0, d_V, sizeof(float) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, s));
   T.kind = kind; T.nEdges = nEdges; T.eV = nV; T.eF = nF; T.eE = nE;
   int* deg = nullptr;   // [nV] degree + [nV] fill cursor
@@ -311,10 +336,24 @@ int edges_forward(const Template& T, int kind, const float* d_V, int nV, const i
   return MO_OK;
 }
 
+// per-incidence records of the stored edge set, built on the first backward pass that needs them
+static int ensure_records(const Template& Tc, cudaStream_t s) {
+  Template& T = const_cast<Template&>(Tc);   // a cache of data derived from the stored edges
+  if (T.d_inc || T.nEdges == 0) return MO_OK;
+  const int nKeys = 2 * T.nEdges;
+  MO_CUDA(dev_alloc(&T.d_inc, (size_t)nKeys, s));
+  if (T.d_lambda) MO_CUDA(dev_alloc(&T.d_inc_lambda, (size_t)nKeys, s));
+  k_csr_records<<<div_up(nKeys, kBlock), kBlock, 0, s>>>(T.d_csr_key, T.d_csr_start, T.eV, T.d_ev, T.d_rest, T.d_lambda,
+                                                         T.d_inc, T.d_inc_lambda);
+  MO_LAUNCH_CHECK();
+  return MO_OK;
+}
+
 int edges_backward(const Template& T, const float* d_V, int nV, float* d_grad, cudaStream_t s) {
   if (nV == 0) return MO_OK;
-  k_edges_backward_csr<<<div_up(nV, kBlock), kBlock, 0, s>>>(d_V, nV, T.d_ev, T.d_rest, T.d_lambda, T.d_csr_start, T.d_csr_key,
-                                                             d_grad);
+  const int rc = ensure_records(T, s);
+  if (rc != MO_OK) return rc;
+  k_edges_backward_csr<<<div_up(nV, kBlock), kBlock, 0, s>>>(d_V, nV, T.d_inc, T.d_inc_lambda, T.d_csr_start, d_grad);
   MO_LAUNCH_CHECK();
   return MO_OK;
 }
@@ -334,9 +373,12 @@ int loss_fused(const Template& TD, const Template* TE, const float* d_V, int nV,
                double* d_loss, float* d_grad, cudaStream_t s) {
   if (d_loss) MO_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(double), s));
   if (nV == 0) return MO_OK;
-  k_loss_fused<<<div_up(nV, kBlock), kBlock, 0, s>>>(TD.d_grid32, TD.N, d_V, nV, TE ? TE->d_ev : nullptr,
-                                                     TE ? TE->d_rest : nullptr, TE ? TE->d_lambda : nullptr,
-                                                     TE ? TE->d_csr_start : nullptr, TE ? TE->d_csr_key : nullptr, w_edge,
+  if (TE) {
+    const int rc = ensure_records(*TE, s);
+    if (rc != MO_OK) return rc;
+  }
+  k_loss_fused<<<div_up(nV, kBlock), kBlock, 0, s>>>(TD.d_grid32, TD.N, d_V, nV, TE ? TE->d_inc : nullptr,
+                                                     TE ? TE->d_inc_lambda : nullptr, TE ? TE->d_csr_start : nullptr, w_edge,
                                                      mask_thr, d_loss, d_grad);
   MO_LAUNCH_CHECK();
   return MO_OK;
