@@ -272,6 +272,27 @@ def SetGrid(param_id, g64, g32, idx, z0=0, z1=None):
                                                 torch.cuda.current_stream().cuda_stream))
 
 
+class _DeviceArray:
+    """A raw device buffer exposed through __cuda_array_interface__ so that torch can alias it."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+def GridViews(param_id):
+    """Additive: torch tensors ALIASING the template's own device fields (grid_f64, grid_f32, nearest), each
+    [N,N,N], for in-place collectives on a z-slab sharded build.  They are views: do not use them after
+    DestroyTemplate, and destroy the derived corner tables by calling SetGrid if the field is changed."""
+    pid = _pid(param_id)
+    N = capi.template_info(pid, torch.cuda.current_stream().cuda_stream)["N"]
+    p64, p32, pidx = capi.template_grid(pid)
+    dev = _device()
+    return (torch.as_tensor(_DeviceArray(p64, (N, N, N), "<f8"), device=dev),
+            torch.as_tensor(_DeviceArray(p32, (N, N, N), "<f4"), device=dev),
+            torch.as_tensor(_DeviceArray(pidx, (N, N, N), "<i4"), device=dev))
+
+
 def NearestVertex(tensorQ, tensorP, return_dist2=False):
     """Additive (ReverseLossLayer): index [nQ] int32 of the nearest row of ``tensorP`` for every row of
     ``tensorQ`` -- scipy's cKDTree(P).query(Q, k=1) on the GPU, exact, FP64 distances."""

@@ -114,6 +114,11 @@ def build_template_sharded(tarV, tarF, grid_resolution, group=None):
     F = tarF.cuda() if not tarF.is_cuda else tarF
     s = torch.cuda.current_stream().cuda_stream
     pid = capi.template_create_slab(V.data_ptr(), V.shape[0], F.data_ptr(), F.shape[0], N, z0, z1, s)
+    if N % world == 0 and dist.get_backend(group) == "nccl":
+        # equal slabs: all-gather IN PLACE on the template's own fields (rank r's slab already sits at offset r)
+        for field in pd.GridViews(pid):
+            dist.all_gather_into_tensor(field, field[z0:z1], group=group)
+        return pid
     g64, g32, idx = pd.GetGrid(pid, z0, z1)
     full64 = allgather_slabs(g64[z0:z1], N, group)
     full32 = allgather_slabs(g32[z0:z1], N, group)

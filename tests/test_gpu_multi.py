@@ -35,15 +35,18 @@ def _worker(rank, world, port, out_dir):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        # ---- z-slab sharded build of one grid (N not divisible by world on purpose when world == 2 -> 50/2) ----
-        N = 50
+        # ---- z-slab sharded build of one grid: equal slabs (in-place all-gather on the template's own fields)
+        #      and ragged slabs (N = 51: padded all-gather) -------------------------------------------------
         V, F = synth_mesh(3000, 11)
         tV, tF = torch.from_numpy(V).to(dev), torch.from_numpy(F).to(dev)
-        pid = sharding.build_template_sharded(tV, tF, N)
-        g64, g32, idx = pd.GetGrid(pid)
-        ref = pd.InitializeDeformTemplate(tV, tF, 0, N)
-        r64, r32, ridx = pd.GetGrid(ref)
-        assert torch.equal(g64, r64) and torch.equal(g32, r32) and torch.equal(idx, ridx)
+        for N in (51, 50):
+            pid = sharding.build_template_sharded(tV, tF, N)
+            g64, g32, idx = pd.GetGrid(pid)
+            ref = pd.InitializeDeformTemplate(tV, tF, 0, N)
+            r64, r32, ridx = pd.GetGrid(ref)
+            assert torch.equal(g64, r64) and torch.equal(g32, r32) and torch.equal(idx, ridx), N
+            if N == 51:
+                pd.DestroyTemplate(pid); pd.DestroyTemplate(ref)
         # the assembled template serves lookups everywhere (a vertex needs slices z and z+1)
         P = torch.rand((4000, 3), device=dev)
         assert torch.equal(pd.DistanceFieldLoss_backward(P, pid), pd.DistanceFieldLoss_backward(P, ref))
