@@ -524,9 +524,10 @@ int ceres_solve(const Template* TD, int kind, double* d_V, double* d_R, int nV, 
   if (cg_tol <= 0.0) cg_tol = 1e-10;
   const size_t ejac_n = rot ? 18 * (size_t)nE : (size_t)nE;
   const int nsc = 16 + 3 * (max_cg + 2);
-  double* buf = nullptr;
   const size_t total = 12 * (size_t)n + 3 * (size_t)nV + ejac_n + nsc;
-  MO_CUDA(cudaMallocAsync(&buf, sizeof(double) * total, s));
+  ScratchBuf<double> scratch;   // released on every exit path
+  MO_CUDA(scratch.alloc(total, s));
+  double* buf = scratch.p;
   double* x = buf; double* xn = x + n; double* g = xn + n; double* diag = g + n; double* scale = diag + n;
   double* damp = scale + n; double* minv = damp + n; double* delta = minv + n; double* r = delta + n;
   double* p = r + n; double* Ap = p + n; double* q = Ap + n; double* gd = q + n; double* ejac = gd + 3 * (size_t)nV;
@@ -576,7 +577,7 @@ int ceres_solve(const Template* TD, int kind, double* d_V, double* d_R, int nV, 
     MO_CUDA(cudaStreamSynchronize(s));
     return MO_OK;
   };
-#define MO_TRY(expr) do { int rc__ = (expr); if (rc__ != MO_OK) { cudaFreeAsync(buf, s); return rc__; } } while (0)
+#define MO_TRY(expr) do { int rc__ = (expr); if (rc__ != MO_OK) return rc__; } while (0)
 
   MO_TRY(evaluate(x, sc, true));
   k_lm_scale<<<gb, 256, 0, s>>>(diag, n, scale);
@@ -667,7 +668,6 @@ int ceres_solve(const Template* TD, int kind, double* d_V, double* d_R, int nV, 
     h_summary[5] = accepted; h_summary[6] = cg_total; h_summary[7] = term; h_summary[8] = radius; h_summary[9] = gmax;
   }
 #undef MO_TRY
-  MO_CUDA(cudaFreeAsync(buf, s));
   return MO_OK;
 }
 

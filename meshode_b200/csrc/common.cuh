@@ -51,6 +51,21 @@ template <class T> inline cudaError_t dev_alloc(T** p, size_t count, cudaStream_
 }
 void dev_free(void* p, cudaStream_t s = 0);
 
+// Stream-ordered scratch that is returned to the pool on every exit path of the function that owns it.
+template <class T>
+struct ScratchBuf {
+  T* p = nullptr;
+  cudaStream_t s = 0;
+  ScratchBuf() = default;
+  ScratchBuf(const ScratchBuf&) = delete;
+  ScratchBuf& operator=(const ScratchBuf&) = delete;
+  ~ScratchBuf() { if (p) cudaFreeAsync(p, s); }
+  cudaError_t alloc(size_t count, cudaStream_t stream) {
+    s = stream;
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream);
+  }
+};
+
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
