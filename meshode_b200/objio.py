@@ -7,7 +7,8 @@ WriteOBJ follows src/lib/mesh.cc:47-64.
 import numpy as np
 
 
-def read_obj(path):
+def read_obj(path, vertex_dtype=np.float32):
+    """``vertex_dtype=np.float64`` keeps the doubles Mesh::ReadOBJ parses (the CAD preprocessing works on them)."""
     V, F = [], []
     with open(path, "r", errors="replace") as fh:
         for line in fh:
@@ -25,7 +26,7 @@ def read_obj(path):
     V = np.asarray(V, dtype=np.float64).reshape(-1, 3)
     F = np.asarray(F, dtype=np.int32).reshape(-1, 3)
     # LoadMesh exports float32 vertices / int32 faces (src/interface/mesh_tensor.cc:87-100)
-    return np.ascontiguousarray(V, dtype=np.float32), np.ascontiguousarray(F, dtype=np.int32)
+    return np.ascontiguousarray(V, dtype=vertex_dtype), np.ascontiguousarray(F, dtype=np.int32)
 
 
 def write_obj(path, V, F):

@@ -81,9 +81,12 @@ def SaveMesh(filename, tensorV, tensorF):
 
 
 def LoadCadMesh(filename):
-    raise NotImplementedError(
-        "LoadCadMesh needs the CGAL-based subdivision (src/lib/subdivision.cc), which is outside the "
-        "GPU hot path (SURVEY.md s8f); build (V, F, E, V2G, GV, GE) on the host and call the loss layers")
+    """src/interface/mesh_tensor.cc:102-178: [V f32 [n,3], F i32 [m,3], E i32 [e,2], V2G i32 [n,1], GV f32 [g,3],
+    GE i32 [ge,2]] -- the CAD mesh cleaned, subdivided to 2e-2 edges, its geometric neighbour pairs (1.5e-2 cells)
+    and its deformation graph (1e-2 cells).  Host code as in the reference, with scipy's Delaunay instead of CGAL's."""
+    from . import cadmesh
+    V, F = read_obj(filename, vertex_dtype=np.float64)
+    return [torch.from_numpy(a) for a in cadmesh.load_cad_mesh(V, F)]
 
 
 def SolveLinear(tensorV, tensorF, tensorE, tensorRef, tensorGraphV, rigidity, with_rot):

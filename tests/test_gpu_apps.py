@@ -131,3 +131,19 @@ def test_python_scripts_mirror_the_reference_cli(tmp_path):
     b0 = _read_obj(str(tmp_path / "b0.obj"))
     assert np.array_equal(b0[0], outs["fused"][0])               # a pair deforms the same alone or in a batch
     assert _read_obj(str(tmp_path / "b1.obj"))[0].shape == tarV.shape
+
+
+def test_cad_deform2_cfg2(tmp_path, meshes):
+    """cfg2 of BASELINE.json: cad_deform2.py data/cad-source.obj -> data/cad-target.obj, rigidity 1, grid 64
+    (a few hundred of the 10 000 iterations): LoadCadMesh, graph + reverse losses on the GPU, SolveLinear, SaveMesh."""
+    import sys
+    s_obj, t_obj, o_obj = (str(tmp_path / x) for x in ("cad-source.obj", "cad-target.obj", "cad-output.obj"))
+    _write_obj(s_obj, meshes["cadSrcV"], meshes["cadSrcF"]); _write_obj(t_obj, meshes["cadTarV"], meshes["cadTarF"])
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cad_deform2.py"), "--source", s_obj, "--target", t_obj,
+                        "--output", o_obj, "--rigidity", "1", "--niter", "301"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    print(p.stdout[-600:])
+    vals = [(float(a), float(b)) for a, b in re.findall(r"loss_src2tar=([0-9.eE+-]+) loss_tar2src=([0-9.eE+-]+)", p.stdout)]
+    assert len(vals) >= 3 and vals[-1][0] < vals[0][0] and vals[-1][1] < vals[0][1]      # both directions improve
+    oV, oF = _read_obj(o_obj)
+    assert oV.shape[0] > meshes["cadSrcV"].shape[0] and np.isfinite(oV).all() and oF.max() < oV.shape[0]
