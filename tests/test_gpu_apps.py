@@ -147,3 +147,19 @@ def test_cad_deform2_cfg2(tmp_path, meshes):
     assert len(vals) >= 3 and vals[-1][0] < vals[0][0] and vals[-1][1] < vals[0][1]      # both directions improve
     oV, oF = _read_obj(o_obj)
     assert oV.shape[0] > meshes["cadSrcV"].shape[0] and np.isfinite(oV).all() and oF.max() < oV.shape[0]
+
+
+def test_cad_neural_deform2(tmp_path, meshes):
+    """The NeuralODE script of cfg5 (cad_neural_deform2.py) on the shipped CAD pair, a few iterations."""
+    import sys
+    s_obj, t_obj, o_obj = (str(tmp_path / x) for x in ("cad-source.obj", "cad-target.obj", "cad-output.obj"))
+    _write_obj(s_obj, meshes["cadSrcV"], meshes["cadSrcF"]); _write_obj(t_obj, meshes["cadTarV"], meshes["cadTarF"])
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cad_neural_deform2.py"), "--source", s_obj, "--target", t_obj,
+                        "--output", o_obj, "--niter", "12", "--save_path", str(tmp_path / "flow.ckpt")], capture_output=True,
+                       text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    tot = [sum(float(x) for x in m) for m in re.findall(
+        r"loss1_forward=([0-9.eE+-]+) loss1_backward=([0-9.eE+-]+) loss2_forward=([0-9.eE+-]+) loss2_backward=([0-9.eE+-]+)", p.stdout)]
+    assert len(tot) == 12 and np.isfinite(tot).all() and tot[-1] < tot[0]
+    oV, oF = _read_obj(o_obj)
+    assert np.isfinite(oV).all() and oF.max() < oV.shape[0] and os.path.exists(str(tmp_path / "flow.ckpt"))
