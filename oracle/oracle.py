@@ -1,6 +1,7 @@
 """ctypes front-end of the CPU oracle (oracle/meshode_oracle.cc).
 
-TEST INFRASTRUCTURE ONLY -- parity unpinned (see the header of meshode_oracle.cc).
+TEST INFRASTRUCTURE ONLY -- sampler, loss functors and Adam are pinned, the nearest-triangle search is
+parity unpinned (see the header of meshode_oracle.cc).
 Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 ``--impl reference`` legs; never by the product package ``meshode_b200``.
 """
