@@ -104,6 +104,9 @@ int edges_backward_atomic(const Template& T, int kind, const float* d_V, int nV,
                           int nE, float* d_grad, cudaStream_t s);
 int loss_fused(const Template& TD, const Template* TE, const float* d_V, int nV, float w_edge, float mask_thr,
                double* d_loss, float* d_grad, cudaStream_t s);
+int adam_loop_coop(const Template& TD, const Template* TE, float* d_V, int nV, float w_edge, float mask_thr,
+                   const float2* d_sched, int iters, float w1, float b2, float w2, float eps, float* d_scratch,
+                   cudaStream_t s);
 
 // ceres_path.cu
 int ceres_edges(int kind, const double* d_V, const double* d_R, int nV, const int* d_I, const double* d_rest, int nE,

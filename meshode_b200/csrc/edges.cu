@@ -166,25 +166,43 @@ __global__ void k_csr_records(const int* __restrict__ keys, const int* __restric
 
 // one vertex's gradient from its records: the same operations in the same (ascending edge, side) order as
 // gather_vertex below, i.e. as the reference's serial scatter loop
+template <bool COHERENT = false>   // COHERENT: V changes during the kernel (persistent loop), read it through L2
 __device__ __forceinline__ void gather_vertex_rec(const float* __restrict__ V, const float self[3],
                                                   const float4* __restrict__ inc, const float* __restrict__ inc_lambda,
                                                   int kb, int ke, float acc[3], double* edge_loss) {
-  for (int i = kb; i < ke; ++i) {
-    const float4 rec = __ldg(inc + i);
-    const unsigned ob = __float_as_uint(rec.w);
-    const int other = (int)(ob & 0x7fffffffu);
-    const bool side = (ob >> 31) != 0u;
-    float lam2 = 1.f, lam = 1.f;
-    if (inc_lambda) { lam = __ldg(inc_lambda + i); lam2 = fmul(lam, lam); }   // cad_layer.cc:186-187
-    const float o[3] = {__ldg(V + 3 * (size_t)other), __ldg(V + 3 * (size_t)other + 1), __ldg(V + 3 * (size_t)other + 2)};
-    const float rs[3] = {rec.x, rec.y, rec.z};
+  constexpr int B = 4;   // incidences whose record and endpoint loads are in flight together (accumulated in order)
+  for (int i0 = kb; i0 < ke; i0 += B) {
+    float4 rec[B];
+    float lamv[B];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      // r = (V[v1] - V[v0]) - rest with (v0, v1) = (self, other) on side 0 and (other, self) on side 1
-      float r = fsub(side ? fsub(self[k], o[k]) : fsub(o[k], self[k]), rs[k]);
-      if (edge_loss && !side) { const float l = inc_lambda ? fmul(r, lam) : r; *edge_loss += (double)fmul(l, l); }
-      if (inc_lambda) r = fmul(r, lam2);
-      acc[k] = side ? fadd(acc[k], r) : fsub(acc[k], r);        // rigid_layer.cc:123-128
+    for (int j = 0; j < B; ++j) {
+      const int i = min(i0 + j, ke - 1);
+      rec[j] = __ldg(inc + i);
+      lamv[j] = inc_lambda ? __ldg(inc_lambda + i) : 1.f;
+    }
+    float o[B][3];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const float* po = V + 3 * (size_t)(__float_as_uint(rec[j].w) & 0x7fffffffu);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[j][k] = COHERENT ? __ldcg(po + k) : __ldg(po + k);
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      if (i0 + j < ke) {
+        const bool side = (__float_as_uint(rec[j].w) >> 31) != 0u;
+        const float lam = lamv[j];
+        const float lam2 = inc_lambda ? fmul(lam, lam) : 1.f;   // cad_layer.cc:186-187
+        const float rs[3] = {rec[j].x, rec[j].y, rec[j].z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          // r = (V[v1] - V[v0]) - rest with (v0, v1) = (self, other) on side 0 and (other, self) on side 1
+          float r = fsub(side ? fsub(self[k], o[j][k]) : fsub(o[j][k], self[k]), rs[k]);
+          if (edge_loss && !side) { const float l = inc_lambda ? fmul(r, lam) : r; *edge_loss += (double)fmul(l, l); }
+          if (inc_lambda) r = fmul(r, lam2);
+          acc[k] = side ? fadd(acc[k], r) : fsub(acc[k], r);        // rigid_layer.cc:123-128
+        }
+      }
     }
   }
 }
@@ -273,7 +291,90 @@ __global__ void __launch_bounds__(kBlock) k_loss_fused(const float* __restrict__
   }
 }
 
+// The whole Adam loop of one mesh of any size in ONE cooperative launch (the launch-bound alternative is two
+// launches per iteration): every thread owns the vertices gtid + k*T, positions are double buffered in global
+// memory (a vertex's new position goes to the other buffer because its neighbours still gather the old one),
+// one grid-wide barrier per iteration.  The arithmetic is k_loss_fused followed by the Adam step of deform.cu,
+// operation for operation.  Vertex reads go through L2 (__ldcg): the read-only path is not coherent with the
+// stores of other SMs.
+__global__ void __launch_bounds__(kBlock) k_adam_loop_coop(const float* __restrict__ grid, int n, float* bufA, float* bufB,
+                                                           int nV, const float4* __restrict__ inc,
+                                                           const float* __restrict__ inc_lambda,
+                                                           const int* __restrict__ start, float w_edge, float mask_thr,
+                                                           const float2* __restrict__ sched, int iters, float w1, float b2,
+                                                           float w2, float eps, float* __restrict__ mom) {
+  cg::grid_group gridg = cg::this_grid();
+  const int T = gridDim.x * kBlock;
+  const int gtid = blockIdx.x * kBlock + threadIdx.x;
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int it = 0; it < iters; ++it) {
+    const float2 sc = __ldg(&sched[it]);
+    for (int v = gtid; v < nV; v += T) {
+      typedef Jet3<float> J;
+      const float p[3] = {__ldcg(cur + 3 * (size_t)v), __ldcg(cur + 3 * (size_t)v + 1), __ldcg(cur + 3 * (size_t)v + 2)};
+      J vd = sample<J, float>(grid, n, J(p[0], 1.f, 0.f, 0.f), J(p[1], 0.f, 1.f, 0.f), J(p[2], 0.f, 0.f, 1.f));
+      vd = vd * vd;
+      const float lossD = fmul(vd.a, 0.5f);
+      float gD[3] = {(float)((double)vd.v0 * 0.5), (float)((double)vd.v1 * 0.5), (float)((double)vd.v2 * 0.5)};
+      if (mask_thr > 0.f && !(lossD < mask_thr)) gD[0] = gD[1] = gD[2] = 0.f;
+      float gE[3] = {0.f, 0.f, 0.f};
+      if (start) gather_vertex_rec<true>(cur, p, inc, inc_lambda, start[v], start[v + 1], gE, nullptr);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float g = fadd(gD[k], fmul(gE[k], w_edge));                    // rigid_loss_layer.py:27
+        float* pm = mom + 3 * (size_t)v + k;
+        float* pv = mom + 3 * (size_t)nV + 3 * (size_t)v + k;
+        const float mi = __fmaf_rn(w1, fsub(g, *pm), *pm);                     // torch's _single_tensor_adam, as k_adam_step
+        const float vi = __fmaf_rn(fmul(w2, g), g, fmul(*pv, b2));
+        *pm = mi; *pv = vi;
+        const float denom = fadd(__fdiv_rn(__fsqrt_rn(vi), sc.y), eps);
+        __stcg(nxt + 3 * (size_t)v + k, fadd(p[k], __fdiv_rn(fmul(sc.x, mi), denom)));
+      }
+    }
+    gridg.sync();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  if (cur != bufA) {   // odd iteration count: the result sits in the scratch buffer
+    for (int i = gtid; i < 3 * nV; i += T) bufA[i] = __ldcg(cur + i);
+  }
+}
+
 }  // namespace
+
+static int ensure_records(const Template& Tc, cudaStream_t s);
+
+// Cooperative persistent Adam loop; returns MO_ERR_STATE when the device cannot co-schedule the grid (the
+// caller then falls back to two launches per iteration).
+int adam_loop_coop(const Template& TD, const Template* TE, float* d_V, int nV, float w_edge, float mask_thr,
+                   const float2* d_sched, int iters, float w1, float b2, float w2, float eps, float* d_scratch,
+                   cudaStream_t s) {
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  MO_CUDA(cudaGetDevice(&dev));
+  MO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return MO_ERR_STATE;
+  MO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  MO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam_loop_coop, kBlock, 0));
+  if (per_sm < 1) return MO_ERR_STATE;
+  if (TE) {
+    const int rc = ensure_records(*TE, s);
+    if (rc != MO_OK) return rc;
+  }
+  const int blocks = std::min(div_up(nV, kBlock), sms * std::min(per_sm, 2));
+  const float* grid = TD.d_grid32;
+  int n = TD.N;
+  float* bufB = d_scratch;                       // [3*nV] second position buffer
+  float* mom = d_scratch + 3 * (size_t)nV;       // [6*nV] Adam moments (zeroed by the caller)
+  const float4* inc = TE ? TE->d_inc : nullptr;
+  const float* incl = TE ? TE->d_inc_lambda : nullptr;
+  const int* start = TE ? TE->d_csr_start : nullptr;
+  void* args[] = {(void*)&grid, (void*)&n, (void*)&d_V, (void*)&bufB, (void*)&nV, (void*)&inc, (void*)&incl, (void*)&start,
+                  (void*)&w_edge, (void*)&mask_thr, (void*)&d_sched, (void*)&iters, (void*)&w1, (void*)&b2, (void*)&w2,
+                  (void*)&eps, (void*)&mom};
+  MO_CUDA(cudaLaunchCooperativeKernel((const void*)k_adam_loop_coop, dim3(blocks), dim3(kBlock), args, 0, s));
+  MO_LAUNCH_CHECK();
+  return MO_OK;
+}
 
 void free_edges(Template& T, cudaStream_t s) {
   dev_free(T.d_ev, s); dev_free(T.d_rest, s); dev_free(T.d_lambda, s); dev_free(T.d_csr_start, s); dev_free(T.d_csr_key, s);
