@@ -312,22 +312,25 @@ __global__ void __launch_bounds__(kBlock) k_adam_loop_coop(const float* __restri
     const float2 sc = __ldg(&sched[it]);
     for (int v = gtid; v < nV; v += T) {
       typedef Jet3<float> J;
+      // everything that does not depend on another load is requested first: the iteration is a chain of L2 round trips
       const float p[3] = {__ldcg(cur + 3 * (size_t)v), __ldcg(cur + 3 * (size_t)v + 1), __ldcg(cur + 3 * (size_t)v + 2)};
+      const int kb = start ? __ldg(start + v) : 0, ke = start ? __ldg(start + v + 1) : 0;
+      float m0[3], v0[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { m0[k] = __ldcg(mom + 3 * (size_t)v + k); v0[k] = __ldcg(mom + 3 * (size_t)nV + 3 * (size_t)v + k); }
       J vd = sample<J, float>(grid, n, J(p[0], 1.f, 0.f, 0.f), J(p[1], 0.f, 1.f, 0.f), J(p[2], 0.f, 0.f, 1.f));
       vd = vd * vd;
       const float lossD = fmul(vd.a, 0.5f);
       float gD[3] = {(float)((double)vd.v0 * 0.5), (float)((double)vd.v1 * 0.5), (float)((double)vd.v2 * 0.5)};
       if (mask_thr > 0.f && !(lossD < mask_thr)) gD[0] = gD[1] = gD[2] = 0.f;
       float gE[3] = {0.f, 0.f, 0.f};
-      if (start) gather_vertex_rec<true>(cur, p, inc, inc_lambda, start[v], start[v + 1], gE, nullptr);
+      if (start) gather_vertex_rec<true>(cur, p, inc, inc_lambda, kb, ke, gE, nullptr);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float g = fadd(gD[k], fmul(gE[k], w_edge));                    // rigid_loss_layer.py:27
-        float* pm = mom + 3 * (size_t)v + k;
-        float* pv = mom + 3 * (size_t)nV + 3 * (size_t)v + k;
-        const float mi = __fmaf_rn(w1, fsub(g, *pm), *pm);                     // torch's _single_tensor_adam, as k_adam_step
-        const float vi = __fmaf_rn(fmul(w2, g), g, fmul(*pv, b2));
-        *pm = mi; *pv = vi;
+        const float mi = __fmaf_rn(w1, fsub(g, m0[k]), m0[k]);                 // torch's _single_tensor_adam, as k_adam_step
+        const float vi = __fmaf_rn(fmul(w2, g), g, fmul(v0[k], b2));
+        __stcg(mom + 3 * (size_t)v + k, mi); __stcg(mom + 3 * (size_t)nV + 3 * (size_t)v + k, vi);
         const float denom = fadd(__fdiv_rn(__fsqrt_rn(vi), sc.y), eps);
         __stcg(nxt + 3 * (size_t)v + k, fadd(p[k], __fdiv_rn(fmul(sc.x, mi), denom)));
       }
