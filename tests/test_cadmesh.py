@@ -69,3 +69,17 @@ def test_delaunay_edges_in_every_dimension():
     vol = rng.uniform(0, 1, (15, 3))
     e3 = cadmesh._delaunay_edges_3d(vol)
     assert len(e3) >= 15 - 1 and (e3[:, 0] < e3[:, 1]).all()
+
+
+def test_mesh_cleanup_rules():
+    """Mesh::RemoveDegenerated (mesh.cc:320-334) and Mesh::MergeDuplex (mesh.cc:181-233)."""
+    from meshode_b200 import cadmesh
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 0, 0.0000001], [2, 0, 0], [0, 0, 1]], dtype=np.float64)
+    F = np.array([[0, 1, 2], [0, 1, 4], [0, 3, 2], [2, 1, 0], [0, 2, 5], [1, 3, 5]], dtype=np.int64)
+    F1 = cadmesh.remove_degenerated(V, F)
+    assert F1.tolist() == [[0, 1, 2], [0, 3, 2], [2, 1, 0], [0, 2, 5], [1, 3, 5]]       # the collinear face goes
+    V2, F2 = cadmesh.merge_duplex(V, F1)
+    # vertex 3 equals vertex 1 after int(v * 1e6); first appearance wins; later indices shift down
+    assert V2.shape == (5, 3) and np.array_equal(V2[3], V[4]) and np.array_equal(V2[4], V[5])
+    # [0,3,2] and [2,1,0] repeat the vertex set of [0,1,2]; [1,3,5] collapses to a repeated vertex
+    assert F2.tolist() == [[0, 1, 2], [0, 2, 4]]
