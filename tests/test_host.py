@@ -79,3 +79,20 @@ def test_golden_fixtures_are_self_consistent(meshes, golden):
     assert meshes["srcV"].shape == (21542, 3) and meshes["srcF"].shape == (43100, 3)      # data/source.obj
     assert golden["grid"].shape == (32, 32, 32) and golden["nearest"].min() >= 0
     assert golden["nearest"].max() < meshes["tarF"].shape[0]
+
+
+def test_scripts_expose_the_reference_command_lines():
+    """scripts/*.py keep the reference scripts' arguments (src/python/rigid_deform.py:15-18, cad_deform2.py:18-22,
+    cad_neural_deform2.py:22-28); --help needs no GPU."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = {"rigid_deform.py": ["--source", "--target", "--output"],
+            "cad_deform2.py": ["--source", "--target", "--output", "--rigidity"],
+            "cad_neural_deform2.py": ["--source", "--target", "--output", "--rigidity", "--device", "--save_path"],
+            "batch_deform.py": ["--filelist", "--niter", "--grid"]}
+    for name, flags in want.items():
+        p = subprocess.run([sys.executable, os.path.join(root, "scripts", name), "--help"], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-1000:]
+        for f in flags:
+            assert f in p.stdout, (name, f)
