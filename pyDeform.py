@@ -2,5 +2,6 @@
 import torch  # noqa: F401  (the reference requires torch to be imported first; README.md:46-50)
 
 from meshode_b200.pyDeform import *  # noqa: F401,F403
-from meshode_b200.pyDeform import (DestroyTemplate, DistanceFieldLoss_forward_backward, EdgeLoss_backward_atomic,  # noqa: F401
-                                   GetGrid, GetTemplateInfo, LossForwardBackward, NearestVertex, SetGrid)
+from meshode_b200.pyDeform import (CeresEdges, CeresProblem, CeresSolve, DestroyTemplate,  # noqa: F401
+                                   DistanceFieldLoss_forward_backward, EdgeLoss_backward_atomic, GetGrid, GetTemplateInfo,
+                                   GridViews, LossForwardBackward, NearestVertex, SetGrid)
