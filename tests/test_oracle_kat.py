@@ -49,6 +49,41 @@ def test_point_triangle_random_vs_sampling(oracle):
         assert d == pytest.approx(((p - q) ** 2).sum(), rel=1e-13)
 
 
+def test_point_triangle_vs_independent_formulation(oracle):
+    """An independent algorithm for the same quantity (not Ericson's region walk): the minimum over the
+    orthogonal projection onto the plane (if it falls inside, by barycentric coordinates from a 2x2 solve),
+    the three clamped edge projections and the three vertices.  libigl is absent, so this is what the
+    nearest-triangle restatement can be held against besides brute-force sampling."""
+    rng = np.random.default_rng(11)
+
+    def seg(p, a, b):
+        ab = b - a
+        t = np.clip(((p - a) @ ab) / max(ab @ ab, 1e-300), 0.0, 1.0)
+        return (((a + t * ab) - p) ** 2).sum()
+
+    worst = 0.0
+    for k in range(4000):
+        a, b, c, p = rng.normal(0, 1, (4, 3))
+        if k % 4 == 1:            # slivers
+            c = a + (b - a) * rng.uniform(-0.5, 1.5) + rng.normal(0, 1e-4, 3)
+        if k % 4 == 2:            # points close to the plane
+            u, v = rng.uniform(-0.3, 1.3, 2)
+            n = np.cross(b - a, c - a)
+            p = a + u * (b - a) + v * (c - a) + 1e-3 * rng.normal() * n / np.linalg.norm(n)
+        cand = [seg(p, a, b), seg(p, b, c), seg(p, c, a)]
+        ab, ac, ap = b - a, c - a, p - a
+        G = np.array([[ab @ ab, ab @ ac], [ab @ ac, ac @ ac]])
+        if abs(np.linalg.det(G)) > 1e-14 * G[0, 0] * G[1, 1]:
+            s, t = np.linalg.solve(G, np.array([ab @ ap, ac @ ap]))
+            if s >= 0 and t >= 0 and s + t <= 1:
+                cand.append((((a + s * ab + t * ac) - p) ** 2).sum())
+        want = min(cand)
+        d, _ = oracle.point_triangle_sqr(p, a, b, c)
+        worst = max(worst, abs(d - want) / max(want, 1e-30))
+        assert abs(d - want) <= 1e-9 * max(want, 1e-12), (k, d, want)
+    print("largest relative difference", worst)
+
+
 # ---- grid build --------------------------------------------------------------------------------
 def test_normalize_target(oracle, meshes):
     V = meshes["tarV"]
