@@ -64,14 +64,29 @@ int mo_template_create(const float* d_V, int nV, const int* d_F, int nF, int sym
 int mo_template_create_slab(const float* d_V, int nV, const int* d_F, int nF, int grid_res, int z0, int z1,
                             mo_stream_t stream, int* out_param_id);
 
+/* Same, cyclic: only the z-tile layers first_layer, first_layer + layer_stride, ... are computed, a layer being
+ * MO_LAYER_SLICES = 4 consecutive voxel slices (layer l = slices [4l, 4l+4)).  With layer_stride = number of
+ * GPUs and first_layer = rank every GPU's share spans the whole z range, so the shares cost the same wherever
+ * the surface lies (contiguous slabs through the middle of a shape cost more than polar ones).  The layers of
+ * group j (slices [4*stride*j, 4*stride*(j+1))) are contiguous in the fields, rank r's piece at offset 4r
+ * slices: one in-place all-gather per group assembles the field. */
+enum { MO_LAYER_SLICES = 4 };
+int mo_template_create_layers(const float* d_V, int nV, const int* d_F, int nF, int grid_res, int first_layer,
+                              int layer_stride, mo_stream_t stream, int* out_param_id);
+
 /* Mesh::ConstructDistanceField on an ALREADY normalised FP64 mesh (the C++ drivers'
  * path: ref.Normalize(); ref.ConstructDistanceField(grid) -- src/app/rigid_deform.cc:49-52).
  * scale/trans are recorded as given (Mesh::GetScale/GetTranslation). */
 int mo_template_create_normalized(const double* d_Vn, int nV, const int* d_F, int nF, int grid_res, double scale,
                                   const double* h_trans3, mo_stream_t stream, int* out_param_id);
 
-/* g_params entries are never freed in the reference (deform_params.cc:7-14); this is additive. */
+/* g_params entries are never freed in the reference (deform_params.cc:7-14); these are additive.
+ * mo_template_destroy waits for the template's device to go idle (work that still reads the template may sit on
+ * any stream) and frees; mo_template_destroy_async returns the buffers to the pool in the order of `stream` --
+ * the caller guarantees that every use of the template was enqueued on, or is ordered before, that stream.
+ * Entry points running concurrently with a destroy keep the template alive until they return. */
 int mo_template_destroy(int param_id);
+int mo_template_destroy_async(int param_id, mo_stream_t stream);
 
 /* Host copies of the template's metadata (Mesh::GetScale / GetTranslation,
  * UniformGrid::Dimension).  Synchronises `stream`.  Any out pointer may be NULL. */
@@ -157,7 +172,11 @@ int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, c
 int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* d_V, int nV, float w_edge,
                              float mask_threshold, double* d_loss, float* d_grad, mo_stream_t stream);
 
-enum { MO_DEFORM_EXACT = 1 };
+enum {
+  MO_DEFORM_EXACT = 1,         /* reference order of the edge sum: bit-identical to the CPU loop */
+  MO_DEFORM_CTA_ONLY = 2,      /* exact loop: never use the cluster-split kernel (A/B timing, tests) */
+  MO_DEFORM_CLUSTER_ONLY = 4   /* exact loop: every pair on the cluster-split kernel (A/B timing, tests) */
+};
 
 /* ---- whole optimisation loops (src/python/rigid_deform.py:32-41) ----------------------- */
 /* For each of B independent pairs: `iters` iterations of
@@ -174,7 +193,11 @@ enum { MO_DEFORM_EXACT = 1 };
  * bench.py use.  flags = 0 (fast, opt-in): the edge term is summed over distinct neighbours on
  * displacements U = V - V0 -- mathematically the same sum, one gather per neighbour, ~1e-10 per
  * term away from the reference's float32 order; Adam amplifies that to ~2e-4 Chamfer after 10 000
- * iterations, exactly what a 1-ulp change of the input does to the exact loop (tools/chaos_probe.py). */
+ * iterations, exactly what a 1-ulp change of the input does to the exact loop (tools/chaos_probe.py).
+ * Scheduling of the exact loop: full waves of pairs run one CTA per pair; the B mod (SM count) pairs of a
+ * partial wave (all of them when B is smaller than the SM count) run on thread-block clusters, ceil(nV/1024)
+ * SMs per pair with the positions exchanged through distributed shared memory, when that finishes sooner.
+ * Same arithmetic, same bits; MO_DEFORM_CTA_ONLY / MO_DEFORM_CLUSTER_ONLY pin one schedule. */
 int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* const* h_dV, int B, int iters,
                          double lr, double beta1, double beta2, double eps, int flags, mo_stream_t stream);
 /* Same loop for one pair of any size (state in HBM/L2, two launches per iteration), with the

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmeshode_b200.so")
 MO_OK = 0
 EDGES_RIGID, EDGES_GRAPH, EDGES_CAD = 0, 1, 2
 CERES_EDGE, CERES_ADAPTIVE_EDGE, CERES_ROT_EDGE = 0, 1, 2
-DEFORM_EXACT = 1
+DEFORM_EXACT, DEFORM_CTA_ONLY, DEFORM_CLUSTER_ONLY = 1, 2, 4
 
 _vp, _i, _d, _f = C.c_void_p, C.c_int, C.c_double, C.c_float
 _ip, _dp, _ullp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)
@@ -27,8 +27,10 @@ SIGNATURES = {
     "mo_microbench_fp32": [_i, _i, _i, _vp, _vp],
     "mo_template_create": [_vp, _i, _vp, _i, _i, _i, _vp, _ip],
     "mo_template_create_slab": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _ip],
+    "mo_template_create_layers": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _ip],
     "mo_template_create_normalized": [_vp, _i, _vp, _i, _i, _d, _dp, _vp, _ip],
     "mo_template_destroy": [_i],
+    "mo_template_destroy_async": [_i, _vp],
     "mo_template_info": [_i, _vp, _ip, _ip, _ip, _dp, _dp],
     "mo_template_grid": [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "mo_template_copy_grid": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -107,6 +109,12 @@ def template_create_slab(dV, nV, dF, nF, N, z0, z1, stream=0):
     return pid.value
 
 
+def template_create_layers(dV, nV, dF, nF, N, first_layer, layer_stride, stream=0):
+    pid = C.c_int(-1)
+    check(lib().mo_template_create_layers(dV, nV, dF, nF, int(N), int(first_layer), int(layer_stride), stream, C.byref(pid)))
+    return pid.value
+
+
 def template_create_normalized(dVn, nV, dF, nF, N, scale, trans, stream=0):
     pid = C.c_int(-1)
     t = (C.c_double * 3)(*[float(x) for x in trans])
@@ -114,8 +122,12 @@ def template_create_normalized(dVn, nV, dF, nF, N, scale, trans, stream=0):
     return pid.value
 
 
-def template_destroy(pid):
-    check(lib().mo_template_destroy(int(pid)))
+def template_destroy(pid, stream=None):
+    """stream=None: waits for the device, then frees; otherwise frees in the order of ``stream``."""
+    if stream is None:
+        check(lib().mo_template_destroy(int(pid)))
+    else:
+        check(lib().mo_template_destroy_async(int(pid), stream))
 
 
 def template_info(pid, stream=0):

@@ -42,23 +42,53 @@ void dev_free(void* p, cudaStream_t s) {
 namespace {
 
 std::mutex g_mutex;
-std::vector<std::unique_ptr<Template>> g_templates;   // index = param_id, like g_params
+std::vector<std::shared_ptr<Template>> g_templates;   // index = param_id, like g_params
 
-Template* lookup(int pid) {
-  std::lock_guard<std::mutex> lock(g_mutex);
-  if (pid < 0 || pid >= (int)g_templates.size() || !g_templates[pid]) {
+// Entry points hold the template through a shared_ptr for the duration of the call, so a concurrent
+// mo_template_destroy cannot pull it from under them (the device buffers go when the last holder lets go).
+// A template belongs to the device it was created on: using it while another device is current is refused
+// here rather than left to fault with an illegal address inside a kernel.
+typedef std::shared_ptr<Template> TemplateRef;
+TemplateRef lookup(int pid) {
+  TemplateRef T;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (pid >= 0 && pid < (int)g_templates.size()) T = g_templates[pid];
+  }
+  if (!T) {
     set_error("bad param_id " + std::to_string(pid));
     return nullptr;
   }
-  return g_templates[pid].get();
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
+  if (dev != T->device) {
+    set_error("param_id " + std::to_string(pid) + " lives on CUDA device " + std::to_string(T->device) +
+              ", the current device is " + std::to_string(dev));
+    return nullptr;
+  }
+  return T;
 }
 
 void release(Template& T, cudaStream_t s = 0) {
   free_edges(T, s);
   dev_free(T.d_Vn, s); dev_free(T.d_F, s); dev_free(T.d_grid64, s); dev_free(T.d_grid32, s); dev_free(T.d_nearest, s);
   dev_free(T.d_xf, s); dev_free(T.d_stats, s); dev_free(T.d_cells, s);
-  T.d_cells = nullptr;
+  T.d_Vn = nullptr; T.d_F = nullptr; T.d_grid64 = nullptr; T.d_grid32 = nullptr; T.d_nearest = nullptr;
+  T.d_xf = nullptr; T.d_stats = nullptr; T.d_cells = nullptr;
 }
+
+// the buffers of a destroyed template go back to the pool in the order of `free_stream` when the last holder
+// (the table or an entry point still running with it) lets go
+struct TemplateDeleter {
+  void operator()(Template* T) const {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != T->device) cudaSetDevice(T->device);
+    release(*T, T->free_stream);
+    if (cur != T->device && cur >= 0) cudaSetDevice(cur);
+    delete T;
+  }
+};
 
 int allocate(Template& T, cudaStream_t s) {
   const size_t nvox = (size_t)T.N * T.N * T.N;
@@ -75,20 +105,21 @@ int allocate(Template& T, cudaStream_t s) {
 
 int publish(std::unique_ptr<Template>& T, int* out) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  g_templates.push_back(std::move(T));
+  g_templates.push_back(TemplateRef(T.release(), TemplateDeleter()));
   *out = (int)g_templates.size() - 1;
   return MO_OK;
 }
 
 int create_common(const float* d_V, const double* d_Vn, int nV, const int* d_F, int nF, int N, int z0, int z1, double scale,
-                  const double* h_trans, cudaStream_t s, int* out) {
+                  const double* h_trans, cudaStream_t s, int* out, int tz_first = 0, int tz_stride = 1) {
   MO_REQUIRE(out != nullptr, "out_param_id is null");
   MO_REQUIRE((d_V != nullptr || d_Vn != nullptr) && d_F != nullptr, "null vertex / face pointer");
   MO_REQUIRE(nV > 0 && nF > 0, "empty mesh");
   MO_REQUIRE(N >= 2 && N <= 1024, "grid_resolution must be in [2, 1024]");
   MO_REQUIRE(0 <= z0 && z0 < z1 && z1 <= N, "bad z-slab");
+  MO_REQUIRE(tz_stride >= 1 && tz_first >= 0 && (tz_stride == 1 ? tz_first == 0 : tz_first < tz_stride), "bad layer selection");
   std::unique_ptr<Template> T(new Template());
-  T->N = N; T->nV = nV; T->nF = nF; T->z0 = z0; T->z1 = z1;
+  T->N = N; T->nV = nV; T->nF = nF; T->z0 = z0; T->z1 = z1; T->tz_first = tz_first; T->tz_stride = tz_stride;
   int rc = allocate(*T, s);
   if (rc != MO_OK) { release(*T, s); return rc; }
   cudaError_t e = cudaMemcpyAsync(T->d_F, d_F, sizeof(int) * 3 * (size_t)nF, cudaMemcpyDeviceToDevice, s);
@@ -142,28 +173,47 @@ int mo_template_create_slab(const float* d_V, int nV, const int* d_F, int nF, in
   return create_common(d_V, nullptr, nV, d_F, nF, grid_res, z0, z1, 1.0, nullptr, (cudaStream_t)stream, out_param_id);
 }
 
+int mo_template_create_layers(const float* d_V, int nV, const int* d_F, int nF, int grid_res, int first_layer, int layer_stride,
+                              mo_stream_t stream, int* out_param_id) {
+  return create_common(d_V, nullptr, nV, d_F, nF, grid_res, 0, grid_res, 1.0, nullptr, (cudaStream_t)stream, out_param_id,
+                       first_layer, layer_stride);
+}
+
 int mo_template_create_normalized(const double* d_Vn, int nV, const int* d_F, int nF, int grid_res, double scale,
                                   const double* h_trans3, mo_stream_t stream, int* out_param_id) {
   return create_common(nullptr, d_Vn, nV, d_F, nF, grid_res, 0, grid_res, scale, h_trans3, (cudaStream_t)stream, out_param_id);
 }
 
-int mo_template_destroy(int param_id) {
-  std::unique_ptr<Template> T;
+static int destroy_common(int param_id, cudaStream_t s, bool device_sync) {
+  TemplateRef T;
   {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (param_id < 0 || param_id >= (int)g_templates.size() || !g_templates[param_id]) {
       set_error("bad param_id " + std::to_string(param_id));
       return MO_ERR_BAD_HANDLE;
     }
-    T = std::move(g_templates[param_id]);
+    T.swap(g_templates[param_id]);
   }
-  // returned to the pool in the order of the legacy default stream (which joins all blocking streams)
-  release(*T, 0);
-  return MO_OK;
+  if (device_sync) {
+    // no stream given: work that still reads the template may sit on any (non-blocking) stream of its device,
+    // which the legacy default stream does not order -- wait for the device, like cudaFree does
+    int cur = -1;
+    MO_CUDA(cudaGetDevice(&cur));
+    if (cur != T->device) MO_CUDA(cudaSetDevice(T->device));
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (cur != T->device) cudaSetDevice(cur);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize", __FILE__, __LINE__);
+  }
+  T->free_stream = s;
+  return MO_OK;   // T goes out of scope: freed now, or when a concurrent entry point drops its reference
 }
 
+int mo_template_destroy(int param_id) { return destroy_common(param_id, 0, true); }
+
+int mo_template_destroy_async(int param_id, mo_stream_t stream) { return destroy_common(param_id, (cudaStream_t)stream, false); }
+
 int mo_template_info(int param_id, mo_stream_t stream, int* grid_res, int* nV, int* nF, double* scale, double* trans3) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   if (grid_res) *grid_res = T->N;
   if (nV) *nV = T->nV;
@@ -179,7 +229,7 @@ int mo_template_info(int param_id, mo_stream_t stream, int* grid_res, int* nV, i
 }
 
 int mo_template_grid(int param_id, const double** d_grid_f64, const float** d_grid_f32, const int** d_nearest) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   if (d_grid_f64) *d_grid_f64 = T->d_grid64;
   if (d_grid_f32) *d_grid_f32 = T->d_grid32;
@@ -189,7 +239,7 @@ int mo_template_grid(int param_id, const double** d_grid_f64, const float** d_gr
 
 int mo_template_copy_grid(int param_id, int direction, int z0, int z1, double* d_grid_f64, float* d_grid_f32,
                           int* d_nearest, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   MO_REQUIRE(0 <= z0 && z0 <= z1 && z1 <= T->N, "bad slice range");
   MO_REQUIRE(direction == 0 || direction == 1, "direction must be 0 or 1");
@@ -213,7 +263,7 @@ int mo_template_copy_grid(int param_id, int direction, int z0, int z1, double* d
 }
 
 int mo_template_vertices(int param_id, const double** d_Vn) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   if (d_Vn) *d_Vn = T->d_Vn;
   return MO_OK;
@@ -221,7 +271,7 @@ int mo_template_vertices(int param_id, const double** d_Vn) {
 
 int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long* fp32_tests, unsigned long long* fp64_tests,
                             unsigned long long* cull_tests, unsigned long long* disc_tests) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   unsigned long long h[8];
   MO_CUDA(cudaMemcpyAsync(h, T->d_stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -239,28 +289,28 @@ int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long
 }
 
 int mo_distance_forward(const float* d_V, int n, int param_id, float* d_out, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   MO_REQUIRE(n >= 0 && (n == 0 || (d_V && d_out)), "null pointer");
   return launch_distance_f32(*T, d_V, n, d_out, nullptr, 1, (cudaStream_t)stream);
 }
 
 int mo_distance_backward(const float* d_V, int n, int param_id, float* d_grad, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   MO_REQUIRE(n >= 0 && (n == 0 || (d_V && d_grad)), "null pointer");
   return launch_distance_f32(*T, d_V, n, nullptr, d_grad, 2, (cudaStream_t)stream);
 }
 
 int mo_distance_forward_backward(const float* d_V, int n, int param_id, float* d_out, float* d_grad, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   MO_REQUIRE(n >= 0 && (n == 0 || (d_V && d_out && d_grad)), "null pointer");
   return launch_distance_f32(*T, d_V, n, d_out, d_grad, 3, (cudaStream_t)stream);
 }
 
 int mo_distance_f64(const double* d_P, int n, int param_id, double* d_val, double* d_grad, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   MO_REQUIRE(n >= 0 && (n == 0 || (d_P && d_val)), "null pointer");
   return launch_distance_f64(*T, d_P, n, d_val, d_grad, (cudaStream_t)stream);
@@ -282,7 +332,7 @@ static void canon(int kind, int& nF, int& nE) {
 
 int mo_edges_store(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
                    mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
   if (rc != MO_OK) return rc;
@@ -299,7 +349,7 @@ static int check_stored(const Template& T, int kind, int nV, int nF, int nE, boo
 
 int mo_edges_forward(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
                      float* d_out, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
   if (rc != MO_OK) return rc;
@@ -312,7 +362,7 @@ int mo_edges_forward(int param_id, int kind, const float* d_V, int nV, const int
 
 int mo_edges_backward(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E, int nE,
                       float* d_grad, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
   if (rc != MO_OK) return rc;
@@ -325,7 +375,7 @@ int mo_edges_backward(int param_id, int kind, const float* d_V, int nV, const in
 
 int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
                              int nE, float* d_grad, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   int rc = check_edge_args(kind, d_V, nV, d_F, nF, d_E, nE);
   if (rc != MO_OK) return rc;
@@ -338,9 +388,9 @@ int mo_edges_backward_atomic(int param_id, int kind, const float* d_V, int nV, c
 
 int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* d_V, int nV, float w_edge,
                              float mask_threshold, double* d_loss, float* d_grad, mo_stream_t stream) {
-  Template* TD = lookup(dist_param_id);
+  const TemplateRef TD = lookup(dist_param_id);
   if (!TD) return MO_ERR_BAD_HANDLE;
-  Template* TE = nullptr;
+  TemplateRef TE;
   if (edge_param_id >= 0) {
     TE = lookup(edge_param_id);
     if (!TE) return MO_ERR_BAD_HANDLE;
@@ -348,7 +398,7 @@ int mo_loss_forward_backward(int dist_param_id, int edge_param_id, const float* 
     MO_REQUIRE(nV == TE->eV, "vertex count differs from the stored one");
   }
   MO_REQUIRE(nV >= 0 && (nV == 0 || d_V), "null pointer");
-  return loss_fused(*TD, TE, d_V, nV, w_edge, mask_threshold, d_loss, d_grad, (cudaStream_t)stream);
+  return loss_fused(*TD, TE.get(), d_V, nV, w_edge, mask_threshold, d_loss, d_grad, (cudaStream_t)stream);
 }
 
 
@@ -356,10 +406,13 @@ int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* 
                          double beta1, double beta2, double eps, int flags, mo_stream_t stream) {
   MO_REQUIRE(B >= 0 && iters >= 0, "negative count");
   MO_REQUIRE(B == 0 || (h_dist_pids && h_edge_pids && h_dV), "null pointer");
+  std::vector<TemplateRef> hold(2 * (size_t)B);
   std::vector<Template*> td(B), te(B);
   for (int i = 0; i < B; ++i) {
-    td[i] = lookup(h_dist_pids[i]);
-    te[i] = lookup(h_edge_pids[i]);
+    hold[2 * i] = lookup(h_dist_pids[i]);
+    hold[2 * i + 1] = lookup(h_edge_pids[i]);
+    td[i] = hold[2 * i].get();
+    te[i] = hold[2 * i + 1].get();
     if (!td[i] || !te[i]) return MO_ERR_BAD_HANDLE;
     MO_REQUIRE(h_dV[i] != nullptr, "null vertex pointer");
   }
@@ -368,8 +421,8 @@ int mo_deform_batch_adam(const int* h_dist_pids, const int* h_edge_pids, float* 
 
 int mo_deform_adam_large(int dist_pid, int edge_pid, float* d_V, int nV, float w_edge, float mask_threshold, int iters,
                          double lr, double beta1, double beta2, double eps, mo_stream_t stream) {
-  Template* TD = lookup(dist_pid);
-  Template* TE = lookup(edge_pid);
+  const TemplateRef TD = lookup(dist_pid);
+  const TemplateRef TE = lookup(edge_pid);
   if (!TD || !TE) return MO_ERR_BAD_HANDLE;
   if (TE->kind == MO_EDGES_NONE) { set_error("no edges stored for edge_pid"); return MO_ERR_STATE; }
   MO_REQUIRE(nV == TE->eV && (nV == 0 || d_V) && iters >= 0, "vertex count differs from the stored one / null pointer");
@@ -393,12 +446,12 @@ int mo_ceres_problem(int dist_param_id, int kind, const double* d_V, const doubl
   MO_REQUIRE(nV == 0 || d_V, "null vertex pointer");
   MO_REQUIRE(nE == 0 || (d_I && d_rest), "null edge pointer");
   MO_REQUIRE(kind != MO_CERES_ROT_EDGE || nE == 0 || d_R, "EdgeLossWithRot needs the rotation parameters");
-  Template* TD = nullptr;
+  TemplateRef TD;
   if (dist_param_id >= 0) {
     TD = lookup(dist_param_id);
     if (!TD) return MO_ERR_BAD_HANDLE;
   }
-  return ceres_problem(TD, kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, d_cost2, d_gV, d_gR, (cudaStream_t)stream);
+  return ceres_problem(TD.get(), kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, d_cost2, d_gV, d_gR, (cudaStream_t)stream);
 }
 
 int mo_ceres_solve(int dist_param_id, int kind, double* d_V, double* d_R, int nV, const int* d_I, const double* d_rest,
@@ -409,17 +462,17 @@ int mo_ceres_solve(int dist_param_id, int kind, double* d_V, double* d_R, int nV
   MO_REQUIRE(nV == 0 || d_V, "null vertex pointer");
   MO_REQUIRE(nE == 0 || (d_I && d_rest), "null edge pointer");
   MO_REQUIRE(kind != MO_CERES_ROT_EDGE || nV == 0 || d_R, "EdgeLossWithRot needs the rotation parameters");
-  Template* TD = nullptr;
+  TemplateRef TD;
   if (dist_param_id >= 0) {
     TD = lookup(dist_param_id);
     if (!TD) return MO_ERR_BAD_HANDLE;
   }
-  return ceres_solve(TD, kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, max_iterations, max_cg_iterations, cg_tolerance, verbose,
+  return ceres_solve(TD.get(), kind, d_V, d_R, nV, d_I, d_rest, nE, lambda, max_iterations, max_cg_iterations, cg_tolerance, verbose,
                      h_summary, (cudaStream_t)stream);
 }
 
 int mo_normalize_by_template(float* d_V, int n, int param_id, int inverse, mo_stream_t stream) {
-  Template* T = lookup(param_id);
+  const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
   MO_REQUIRE(n >= 0 && (n == 0 || d_V), "null pointer");
   if (n == 0) return MO_OK;

@@ -15,8 +15,10 @@ namespace mo {
 // What DeformParams holds in the reference (src/interface/deform_params.h:7-25), as device buffers.
 struct Template {
   int device = 0;
+  cudaStream_t free_stream = 0;   // the buffers return to the pool in this stream's order (set by mo_template_destroy*)
   int N = 0, nV = 0, nF = 0;
-  int z0 = 0, z1 = 0;
+  int z0 = 0, z1 = 0;           // voxel slices this template's build computes (z-slab sharding)
+  int tz_first = 0, tz_stride = 1;   // or: z-tile layers (4 slices each) tz_first, tz_first + tz_stride, ... (cyclic sharding)
   double* d_Vn = nullptr;       // [nV,3] normalised FP64 target vertices (Mesh::V_ after Normalize)
   int* d_F = nullptr;           // [nF,3]
   double* d_grid64 = nullptr;   // [N^3] z,y,x  (UniformGrid::voxel_distance_)

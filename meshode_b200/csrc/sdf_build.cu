@@ -54,7 +54,7 @@ constexpr float kErrA = 1.2e-5f;
 constexpr float kErrB = 1.2e-9f;
 
 struct SdfArgs {
-  int N, nc, ncc, ntile, tz0, z0, z1;
+  int N, nc, ncc, ntile, tz0, tz_stride, z0, z1;   // tile layers tz0, tz0 + tz_stride, ... ; voxel slices [z0, z1) are stored
   float ccs;                      // coarse cell size in normalised units
   const unsigned* max_ext;        // bit pattern of the largest triangle AABB extent
   const int* coarse_cnt;          // [ncoarse] triangles binned into the coarse cell
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = A.N, ncc = A.ncc;
-  const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile, tz = A.tz0 + blockIdx.x / (A.ntile * A.ntile);   // tz in units of kTileZ
+  const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile, tz = A.tz0 + (blockIdx.x / (A.ntile * A.ntile)) * A.tz_stride;   // tz in units of kTileZ
 
   // this lane's voxel; the warp owns a 4x4x2 block of the tile
   const int bx = tx * kTile + (warp & 1) * 4, by = ty * kTile + ((warp >> 1) & 1) * 4, bz = tz * kTileZ + (warp >> 2) * 2;
@@ -778,15 +778,18 @@ int run_build(Template& T, cudaStream_t s) {
   k_cluster<<<div_up((long long)ncell * 32, 256), 256, 0, s>>>(cl_sc, (int)ncell, rec64, cl_c, cl_n);
   MO_LAUNCH_CHECK();
 
-  if (T.z0 > 0 || T.z1 < N) {
+  if (T.z0 > 0 || T.z1 < N || T.tz_stride > 1) {
     k_fill_grid<<<div_up((long long)nvox, 256), 256, 0, s>>>(T.d_grid64, T.d_grid32, T.d_nearest, nvox);
     MO_LAUNCH_CHECK();
   }
 
   SdfArgs A;
   A.N = N; A.nc = nc; A.ncc = ncc; A.ntile = ntile; A.z0 = T.z0; A.z1 = T.z1;
-  A.tz0 = T.z0 / kTileZ;
-  const int tz1 = (T.z1 - 1) / kTileZ;
+  // slab: the tile layers that hold slices [z0, z1); cyclic: layers tz_first, tz_first + tz_stride, ...
+  A.tz0 = T.tz_stride > 1 ? T.tz_first : T.z0 / kTileZ;
+  A.tz_stride = std::max(T.tz_stride, 1);
+  const int n_layers = T.tz_stride > 1 ? (T.tz_first < div_up(N, kTileZ) ? div_up(div_up(N, kTileZ) - T.tz_first, T.tz_stride) : 0)
+                                       : (T.z1 - 1) / kTileZ - A.tz0 + 1;
   A.ccs = (float)((double)(kCellVox * kCoarse) / N);
   A.max_ext = max_ext; A.coarse_cnt = coarse_cnt; A.coarse_bb = coarse_bb;
   A.cl_sc = cl_sc; A.cl_c = cl_c; A.cl_n = cl_n;
@@ -797,9 +800,11 @@ int run_build(Template& T, cudaStream_t s) {
     MO_CUDA(cudaFuncSetAttribute(k_sdf_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem));
     attr_set[T.device & 63] = true;
   }
-  const int ntiles = ntile * ntile * (tz1 - A.tz0 + 1);
-  k_sdf_tiles<<<ntiles, kThreads, kSdfSmem, s>>>(A);
-  MO_LAUNCH_CHECK();
+  const int ntiles = ntile * ntile * n_layers;
+  if (ntiles > 0) {
+    k_sdf_tiles<<<ntiles, kThreads, kSdfSmem, s>>>(A);
+    MO_LAUNCH_CHECK();
+  }
   MO_CUDA(cudaFreeAsync(scratch, s));
   return MO_OK;
 }

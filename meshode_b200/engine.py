@@ -16,12 +16,18 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def deform_batch_adam(V_list, dist_pids, edge_pids, iters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, exact=True):
+_SCHEDULES = {"auto": 0, "cta": capi.DEFORM_CTA_ONLY, "cluster": capi.DEFORM_CLUSTER_ONLY}
+
+
+def deform_batch_adam(V_list, dist_pids, edge_pids, iters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, exact=True,
+                      schedule="auto"):
     """In-place Adam optimisation of each normalised source ``V_list[i]`` (CUDA float32 [n_i,3])
     against template ``dist_pids[i]`` with the edges stored in template ``edge_pids[i]``.
     ``exact=True`` (default) reproduces the float32 CPU loop bit for bit; ``exact=False`` sums the edge
     term over distinct neighbours (same value to ~1e-10 per term, 1.4x faster), which Adam's chaotic
-    sensitivity turns into ~2e-4 Chamfer after 10 000 iterations -- the same as a 1-ulp change of the input."""
+    sensitivity turns into ~2e-4 Chamfer after 10 000 iterations -- the same as a 1-ulp change of the input.
+    ``schedule`` (exact loop): "auto" runs full waves one CTA per pair and a partial wave on thread-block clusters
+    (several SMs per pair); "cta" / "cluster" pin one of the two kernels.  Same bits either way."""
     B = len(V_list)
     assert len(dist_pids) == B and len(edge_pids) == B
     for v in V_list:
@@ -31,7 +37,7 @@ def deform_batch_adam(V_list, dist_pids, edge_pids, iters, lr=1e-3, betas=(0.9, 
     ep = (C.c_int * B)(*[int(p) for p in edge_pids])
     vp = (C.c_void_p * B)(*[v.data_ptr() for v in V_list])
     capi.check(capi.lib().mo_deform_batch_adam(dp, ep, vp, B, int(iters), float(lr), float(betas[0]), float(betas[1]),
-                                               float(eps), capi.DEFORM_EXACT if exact else 0, _stream()))
+                                               float(eps), (capi.DEFORM_EXACT | _SCHEDULES[schedule]) if exact else 0, _stream()))
 
 
 def deform_adam_large(V, dist_pid, edge_pid, iters, lr=1e-3, w_edge=1.0, mask_threshold=0.0, betas=(0.9, 0.999),
@@ -84,13 +90,13 @@ class PairBatch:
                 t.record_stream(main)
             self._keep = []
 
-    def deform(self, iters=10000, lr=1e-3, exact=True):
+    def deform(self, iters=10000, lr=1e-3, exact=True, schedule="auto"):
         with torch.cuda.device(self.device):
             small = [i for i, v in enumerate(self.V) if v.shape[0] <= 6144]
             large = [i for i, v in enumerate(self.V) if v.shape[0] > 6144]
             if small:
                 deform_batch_adam([self.V[i] for i in small], [self.pids[i] for i in small], [self.pids[i] for i in small],
-                                  iters, lr, exact=exact)
+                                  iters, lr, exact=exact, schedule=schedule)
             for i in large:
                 deform_adam_large(self.V[i], self.pids[i], self.pids[i], iters, lr)
 

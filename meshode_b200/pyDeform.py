@@ -121,9 +121,15 @@ def InitializeDeformTemplate(tensorV, tensorF, symmetry, grid_resolution):
                                     _stream(V))
 
 
-def DestroyTemplate(param_id):
-    """Additive: frees the device buffers of a template (the reference never frees g_params)."""
-    capi.template_destroy(_pid(param_id))
+def DestroyTemplate(param_id, stream_ordered=True):
+    """Additive: frees the device buffers of a template (the reference never frees g_params).
+    ``stream_ordered`` (default): the buffers return to the pool in the order of torch's CURRENT stream, so every
+    use of the template must have been enqueued on it or be ordered before it (``wait_stream``) -- the same rule
+    torch's caching allocator applies to tensors.  ``stream_ordered=False`` waits for the device instead."""
+    if stream_ordered and torch.cuda.is_available():
+        capi.template_destroy(_pid(param_id), torch.cuda.current_stream().cuda_stream)
+    else:
+        capi.template_destroy(_pid(param_id))
 
 
 def _normalize(tensorV, param_id, inverse):

@@ -14,21 +14,22 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 500
 verts = int(sys.argv[3]) if len(sys.argv) > 3 else 5000
 exact = os.environ.get("MESHODE_EXACT", "0") == "1"
+schedule = os.environ.get("MESHODE_SCHEDULE", "auto")   # auto | cta | cluster
 dev = "cuda:0"
 pairs = [tuple(torch.from_numpy(a).to(dev) for a in synth_pair(i, verts, verts)) for i in range(n)]
 res = []
 for rep in range(3):
     b = engine.PairBatch(pairs, 64)
-    b.deform(iters=1, exact=exact)   # builds the adjacency and the cell records (not part of the kernel timing)
+    b.deform(iters=1, exact=exact, schedule=schedule)   # builds the adjacency and the cell records (not part of the kernel timing)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    b.deform(iters=iters, exact=exact)
+    b.deform(iters=iters, exact=exact, schedule=schedule)
     e1.record()
     torch.cuda.synchronize()
     res.append(e0.elapsed_time(e1))
     b.release()
 ms = min(res)
 waves = -(-n // 148)
-print("exact=%s threads=%s pairs=%d iters=%d verts=%d: %.2f ms -> %.2f us per pair-iteration per SM" %
-      (exact, os.environ.get("MESHODE_DEFORM_THREADS", "default"), n, iters, verts, ms, ms * 1e3 / (waves * iters)))
+print("exact=%s schedule=%s pairs=%d iters=%d verts=%d: %.2f ms -> %.2f us per iteration of a full wave (%.2f us per pair-iteration)" %
+      (exact, schedule, n, iters, verts, ms, ms * 1e3 / (waves * iters), ms * 1e3 / (n * iters)))
