@@ -2,11 +2,12 @@
 """bench.py -- deformation pairs/sec (BASELINE.json metric) on N B200s of one node, plus the
 128^3 distance-field build.
 
-A *step* is one pass of the hot path over this rank's batch of synthetic shape pairs (cfg4 of
-BASELINE.json: grid 64, 5 000-vertex meshes, rigid loss, Adam lr 1e-3 x 10 000 iterations):
-for every pair InitializeDeformTemplate (normalise + distance field), NormalizeByTemplate,
-StoreRigidityInformation, the fused Adam loop, DenormalizeByTemplate.  Pairs are independent, so
-ranks shard them with no data-path collective (weak scaling: every rank owns --pairs pairs).
+A *step* is one pass of the hot path over the whole batch of synthetic shape pairs (cfg4 of
+BASELINE.json: 3 625 pairs, grid 64, 5 000-vertex meshes, rigid loss, Adam lr 1e-3 x 10 000
+iterations): for every pair InitializeDeformTemplate (normalise + distance field),
+NormalizeByTemplate, StoreRigidityInformation, the fused Adam loop, DenormalizeByTemplate.  Pairs are
+independent, so the ranks shard the 3 625 pairs in contiguous blocks with no data-path collective
+(STRONG scaling: the total is fixed, rank r owns pairs [floor(r*P/N), floor((r+1)*P/N))).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -14,6 +15,7 @@ ranks shard them with no data-path collective (weak scaling: every rank owns --p
 itself cannot be compiled here) on the host cores for the same metric.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -46,21 +48,30 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=3625, help="pairs per rank and step (cfg4: 3625)")
+    ap.add_argument("--pairs", type=int, default=3625, help="pairs per step IN TOTAL, sharded over the ranks (cfg4: 3625)")
     ap.add_argument("--verts", type=int, default=5000)
     ap.add_argument("--grid", type=int, default=64)
     ap.add_argument("--iters", type=int, default=10000)
     ap.add_argument("--no-sdf128", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of wall clock for the CPU baseline sample")
+    ap.add_argument("--no-slab", action="store_true", help="skip the z-sharded 256^3 build block of multi-GPU runs")
+    ap.add_argument("--no-percall", action="store_true", help="skip the per-iteration (torch.optim.Adam) path block")
     return ap.parse_args()
 
 
-def config_of(a):
-    return {"workload": "cfg4: %d synthetic shape pairs per GPU, %d-vertex source / %d-triangle target, grid %d^3, "
-                        "rigid loss, Adam lr 1e-3 x %d iterations" % (a.pairs, a.verts, 2 * a.verts - 4, a.grid, a.iters),
-            "pairs_per_gpu": a.pairs, "verts": a.verts, "grid": a.grid, "adam_iters": a.iters,
-            "l2": "inputs (%.2f GB per step) exceed the 126 MB L2; no explicit flush" %
+def shard_counts(n, world):
+    return [(n * (r + 1)) // world - (n * r) // world for r in range(world)]
+
+
+def config_of(a, world=None):
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    cnt = shard_counts(a.pairs, world)
+    return {"workload": "cfg4: %d synthetic shape pairs in total (contiguous blocks over %d GPU%s, %d-%d per GPU), %d-vertex "
+                        "source / %d-triangle target, grid %d^3, rigid loss, Adam lr 1e-3 x %d iterations" %
+                        (a.pairs, world, "" if world == 1 else "s", min(cnt), max(cnt), a.verts, 2 * a.verts - 4, a.grid, a.iters),
+            "pairs_total": a.pairs, "pairs_per_gpu": cnt, "verts": a.verts, "grid": a.grid, "adam_iters": a.iters,
+            "l2": "inputs (%.2f GB per step in total) exceed the 126 MB L2; no explicit flush" %
                   (a.pairs * (a.verts * 12 * 2 + (2 * a.verts - 4) * 12 * 2) / 1e9)}
 
 
@@ -89,6 +100,7 @@ def cpu_sample(a, budget_s, pairs_offset=0):
     t_it = (time.perf_counter() - t0) / 50
     it_sample = int(max(50, min(a.iters, (budget_s - t_build) / max(t_it, 1e-9))))
     times = [None] * cores
+    first = [None]
 
     def work(i):
         sV, sF, tV, tF = pairs[i]
@@ -98,9 +110,11 @@ def cpu_sample(a, budget_s, pairs_offset=0):
         r = O.store_rigid(sn, sF)
         t1 = time.perf_counter()
         V, _ = O.rigid_adam(T.grid, sn, sF, r, it_sample, 1e-3)
-        O.denormalize_by_template(V, T.scale, T.trans)
+        out = O.denormalize_by_template(V, T.scale, T.trans)
         t2 = time.perf_counter()
         times[i] = (t1 - t0, t2 - t1)
+        if i == 0:
+            first[0] = out
 
     th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
     t0 = time.perf_counter()
@@ -116,7 +130,7 @@ def cpu_sample(a, budget_s, pairs_offset=0):
     desc = ("%d pairs, one per host thread (ctypes releases the GIL): full grid-%d build (%.2f s) + %d of %d Adam "
             "iterations (scaled x%.2f -> %.2f s) per pair; wall %.1f s" %
             (cores, a.grid, build, it_sample, a.iters, a.iters / it_sample, adam, wall))
-    return value, desc, cores
+    return value, desc, cores, {"pair": pairs_offset, "iters": it_sample, "V": first[0]}
 
 
 def run_reference(a):
@@ -127,13 +141,13 @@ def run_reference(a):
     budget = max(4.0, min(a.cpu_budget, 150.0 / max(n_steps, 1)))
     vals, desc, cores = [], "", 1
     for s in range(n_steps):
-        v, desc, cores = cpu_sample(a, budget, pairs_offset=0)
+        v, desc, cores, _ = cpu_sample(a, budget, pairs_offset=0)
         if s >= a.warmup:
             vals.append(v)
     value = float(np.mean(vals)) if vals else float("nan")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * (os.cpu_count() or 1) / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(a),
+            "warmup": a.warmup, "ms_per_step": 1e3 * a.pairs / value, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(a),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -200,13 +214,205 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def _sha(t):
+    return hashlib.sha256(t.detach().cpu().numpy().tobytes()).hexdigest()
+
+
+def sdf128_block(a, dev, ev, with_cpu):
+    """Secondary metric M1: the 128^3 distance-field build on a 50 000-triangle target (cfg3's target)."""
+    import torch
+    from meshode_b200 import capi
+    from meshode_b200 import pyDeform as pd
+    from meshode_b200.synth import synth_mesh
+    V, F = synth_mesh(25002, 1)
+    tV, tF = torch.from_numpy(V).to(dev), torch.from_numpy(F).to(dev)
+    sink = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    # FP32 denominator: FFMA chain, 8 CTAs of 256 threads per SM
+    it_f = 20000
+    for _ in range(2):
+        capi.check(capi.lib().mo_microbench_fp32(148 * 8, 256, it_f, sink.data_ptr(), s))
+    f0, f1 = ev(), ev()
+    f0.record()
+    capi.check(capi.lib().mo_microbench_fp32(148 * 8, 256, it_f, sink.data_ptr(), s))
+    f1.record()
+    torch.cuda.synchronize()
+    fp32_tf = 148 * 8 * 256 * it_f * 8 * 2 / (f0.elapsed_time(f1) * 1e-3) / 1e12
+    times, stats = [], None
+    for k in range(3 + 5):
+        b0, b1 = ev(), ev()
+        b0.record()
+        pid = pd.InitializeDeformTemplate(tV, tF, 0, 128)
+        b1.record()
+        torch.cuda.synchronize()
+        if k >= 3:
+            times.append(b0.elapsed_time(b1))
+        stats = capi.template_build_stats(pid)
+        pd.DestroyTemplate(pid)
+    ms = float(np.mean(times))
+    flop_tests = stats["fp32_tests"] * FLOP_PER_TEST
+    flop = flop_tests + (stats["cull_tests"] + stats["disc_tests"]) * FLOP_PER_BOUND_TEST
+    tf = flop / (ms * 1e-3) / 1e12
+    tf_tests = flop_tests / (ms * 1e-3) / 1e12
+    blk = {
+        "metric": "grid-SDF build ms at 128^3", "value": ms, "unit": "ms", "target_triangles": int(F.shape[0]),
+        "fp32_tests": stats["fp32_tests"], "cluster_tests": stats["cull_tests"], "disc_tests": stats["disc_tests"],
+        "fp64_tests": stats["fp64_tests"],
+        "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": tf / fp32_tf,
+                     "fp32_frac_tests_only": tf_tests / fp32_tf, "traffic": None,
+                     "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 "
+                                    "entry); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                     "note": "achieved = (point-triangle tests executed x 74 + bounding-cylinder tests of clusters and "
+                             "bounding-disc pre-tests of triangles x 38 FLOP, all counted by the kernel) / build time "
+                             "including binning; fp32_frac_tests_only counts the point-triangle tests alone (SURVEY s8d "
+                             "accounting).  The build is fast because it avoids the brute-force tests (N^3*M*74 = %.3g FLOP = "
+                             "%.0f TFLOP/s equivalent), not because it saturates the FMA pipe" %
+                             (128 ** 3 * F.shape[0] * 74.0, 128 ** 3 * F.shape[0] * 74.0 / (ms * 1e-3) / 1e12)}}
+    if with_cpu:
+        # CPU beside it: the oracle's exact cell-index build of every 8th voxel slice, one slice per host thread,
+        # scaled to the 128 slices (a full build takes ~50 s on 8 cores)
+        from oracle import oracle as O
+        O.lib()
+        Vn, _, _ = O.normalize_target(V)
+        cores = os.cpu_count() or 1
+        slices = list(range(4, 128, 8))
+        t_sl = [0.0] * len(slices)
+
+        def one(k):
+            t0 = time.perf_counter()
+            O.build_grid(Vn, F, 128, z0=slices[k], z1=slices[k] + 1, threads=1, want_idx=False)
+            t_sl[k] = time.perf_counter() - t0
+
+        t0 = time.perf_counter()
+        for base in range(0, len(slices), cores):
+            th = [threading.Thread(target=one, args=(k,)) for k in range(base, min(base + cores, len(slices)))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        wall = time.perf_counter() - t0
+        core_s = float(np.sum(t_sl)) * (128 / len(slices))
+        blk["cpu_baseline"] = {"value": 1e3 * core_s / cores, "unit": "ms", "cores": cores, "kind": "port",
+                               "sample": "oracle exact cell-index build (stands in for libigl's AABB tree) of voxel slices "
+                                         "z = 4, 12, ..., 124 (16 of 128), one slice per host thread, %.1f core-seconds scaled "
+                                         "x8 and divided by the %d cores; wall %.1f s" % (float(np.sum(t_sl)), cores, wall)}
+    return blk, fp32_tf
+
+
+def percall_block(a, dev, ev):
+    """The per-iteration path a user of the reference's scripts takes (src/python/rigid_deform.py:25-44): RigidLossLayer
+    + torch.optim.Adam, one fused loss launch + autograd + the optimiser's kernels per iteration."""
+    import torch
+    from meshode_b200.layers.loss_layers import Finalize, RigidLossLayer
+    from meshode_b200.synth import synth_pair
+    srcV, srcF, tarV, tarF = [torch.from_numpy(x).to(dev) for x in synth_pair(0, a.verts, a.verts)]
+    e0, e1, e2 = ev(), ev(), ev()
+    e0.record()
+    layer = RigidLossLayer(srcV, srcF, tarV, tarF, grid_resolution=a.grid, device=dev)
+    param = torch.nn.Parameter(srcV.clone())
+    # srcV was normalised in place by the layer, as in the reference
+    optimizer = torch.optim.Adam([param], lr=1e-3)
+    n_it = 300
+
+    def loop(n):
+        for _ in range(n):
+            optimizer.zero_grad()
+            loss = layer(param, srcF)
+            loss.backward()
+            optimizer.step()
+
+    loop(30)
+    e1.record()
+    loop(n_it)
+    e2.record()
+    torch.cuda.synchronize()
+    Finalize(param, layer.param_id)
+    us_it = 1e3 * e1.elapsed_time(e2) / n_it
+    setup_ms = e0.elapsed_time(e1) - 30 * us_it * 1e-3
+    pair_s = (setup_ms * 1e-3 + a.iters * us_it * 1e-6)
+    return {"what": "RigidLossLayer + torch.optim.Adam, one pair at a time (the reference script's loop, rigid_deform.py:32-41)",
+            "us_per_iteration": us_it, "iterations_timed": n_it, "pairs_per_s": 1.0 / pair_s,
+            "note": "per iteration: 1 fused loss launch (mo_loss_forward_backward) + autograd + torch's Adam kernels, all "
+                    "enqueued from Python; launch-bound, which is why the headline path is one persistent kernel per batch"}
+
+
+def slab_block(a, dev, ev, rank, world, barrier):
+    """cfg5: ONE 256^3 field on a 500 000-triangle target, built z-sharded over the ranks (cyclic z-tile layers, in-place
+    NCCL all-gather), then the GraphLoss2 loss of cad_neural_deform2.py:40-108 on it."""
+    import torch
+    import torch.distributed as dist
+    from meshode_b200 import pyDeform as pd
+    from meshode_b200 import sharding
+    from meshode_b200.layers.loss_layers import _FusedLoss
+    from meshode_b200.synth import synth_mesh, unique_edges
+    N = 256
+    V, F = synth_mesh(250002, 1)
+    tV, tF = torch.from_numpy(V).to(dev), torch.from_numpy(F).to(dev)
+    res = []
+    pid = None
+    for k in range(2 + 3):
+        if pid is not None:
+            pd.DestroyTemplate(pid)
+        barrier()
+        pid, tm = sharding.build_template_sharded(tV, tF, N, timings=True)
+        torch.cuda.synchronize()
+        if k >= 2:
+            res.append(tm)
+    t = torch.tensor([[r["build_ms"], r["gather_ms"], r["total_ms"]] for r in res], dtype=torch.float64, device=dev).mean(0)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tmin = t.clone()
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    # the same field on one GPU, for the speed-up and for bit-equality (every rank checks its own copy)
+    ref_ms = []
+    ref = None
+    for k in range(3):
+        if ref is not None:
+            pd.DestroyTemplate(ref)
+        b0, b1 = ev(), ev()
+        b0.record()
+        ref = pd.InitializeDeformTemplate(tV, tF, 0, N)
+        b1.record()
+        torch.cuda.synchronize()
+        ref_ms.append(b0.elapsed_time(b1))
+    same = all(torch.equal(x, y) for x, y in zip(pd.GridViews(pid), pd.GridViews(ref)))
+    ok = torch.tensor([1 if same else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    pd.DestroyTemplate(ref)
+    # GraphLoss2-style loss on the assembled field: 20 000-node graph, one fused launch (forward + backward)
+    gV, gF = synth_mesh(20000, 2, axis_scale=None)
+    gE = torch.from_numpy(unique_edges(gF)).to(dev)
+    g = torch.from_numpy(gV).to(dev)
+    pd.NormalizeByTemplate(g, pid)
+    pd.StoreGraphInformation(g, gE, pid)
+    moved = (g + 1e-3 * torch.sin(31.0 * g)).contiguous().requires_grad_(True)
+    for _ in range(5):
+        _FusedLoss.apply(moved, pid, pid, 1.0, 0.0)
+    l0, l1 = ev(), ev()
+    l0.record()
+    for _ in range(50):
+        _FusedLoss.apply(moved, pid, pid, 1.0, 0.0)
+    l1.record()
+    torch.cuda.synchronize()
+    pd.DestroyTemplate(pid)
+    return {"metric": "256^3 distance field on a 500 000-triangle target, z-sharded over %d GPUs" % world,
+            "value": float(tmax[2]), "unit": "ms", "slab_build_ms_slowest_rank": float(tmax[0]),
+            "slab_build_ms_fastest_rank": float(tmin[0]), "all_gather_ms": float(tmax[1]),
+            "single_gpu_ms": float(np.mean(ref_ms[1:])), "speedup_vs_single_gpu": float(np.mean(ref_ms[1:])) / float(tmax[2]),
+            "sharding": res[0]["mode"], "parity": "bit-identical to the single-GPU build (all three fields, every rank)"
+            if int(ok.item()) == 1 else "MISMATCH",
+            "graph_loss_us": 1e3 * l0.elapsed_time(l1) / 50,
+            "graph_loss_note": "GraphLoss2-style fused forward+backward (distance + graph edges) for a 20 000-node graph "
+                               "on the assembled 256^3 field, through autograd.Function, per call"}
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
 
     from meshode_b200 import capi, engine
-    from meshode_b200 import pyDeform as pd
-    from meshode_b200.synth import synth_mesh, synth_pair
+    from meshode_b200.sharding import shard_range
+    from meshode_b200.synth import synth_pair
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,23 +429,23 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- synthetic inputs: pinned host copies and resident device copies ------------------------
-    n = a.pairs
-    first = rank * n
+    # ---- synthetic inputs: pinned host copies and resident device copies of this rank's block ---------
+    lo, hi = shard_range(a.pairs, rank, world)
+    n = hi - lo
     host_pairs = []
-    for i in range(n):
-        arrs = synth_pair(first + i, a.verts, a.verts)
+    for i in range(lo, hi):
+        arrs = synth_pair(i, a.verts, a.verts)
         host_pairs.append(tuple(torch.from_numpy(x).pin_memory() for x in arrs))
     dev_pairs = [tuple(t.to(dev) for t in p) for p in host_pairs]
     nV = a.verts
-    nE = 3 * host_pairs[0][1].shape[0]
+    nE = 3 * (2 * a.verts - 4)
     h2d = sum(t.numel() * t.element_size() for p in host_pairs for t in p)
     d2h = sum(p[0].numel() * 4 for p in host_pairs)
     host_out = [torch.empty_like(p[0]).pin_memory() for p in host_pairs]
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    deform_ms = []
+    keep = {}
 
     def step(pairs, e2e=False):
         batch = engine.PairBatch(pairs, grid_resolution=a.grid, device=dev)
@@ -251,6 +457,8 @@ def run_b200(a):
         if e2e:
             for o, h in zip(out, host_out):
                 h.copy_(o, non_blocking=True)
+        if out:
+            keep["first"] = out[0]
         batch.release()
         return e0, e1
 
@@ -274,6 +482,7 @@ def run_b200(a):
     clk = clocks.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
     deform_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    first_hash = _sha(keep["first"]) if n > 0 else ""
 
     # ---- timed: end to end from pinned host buffers ----------------------------------------------------
     step(host_pairs, e2e=True)
@@ -287,13 +496,38 @@ def run_b200(a):
     barrier()
     ms_e2e = t_start2.elapsed_time(t_end2) / n_e2e
 
+    t = torch.tensor([ms_total, ms_e2e, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = t.tolist()
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms_total, ms_e2e = tm[0].item(), tm[1].item()
+        launches = int(ts[2].item())
+        hh = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+        dist.all_reduce(hh, op=dist.ReduceOp.SUM)
+        h2d, d2h = int(hh[0].item()), int(hh[1].item())
     ms_step = ms_total / a.steps
-    value = world * n / (ms_step * 1e-3)
-    e2e_value = world * n / (ms_e2e * 1e-3)
+    value = a.pairs / (ms_step * 1e-3)
+    e2e_value = a.pairs / (ms_e2e * 1e-3)
+
+    # ---- results across devices and schedules: every rank recomputes the first pair of the NEXT rank's block on its own
+    #      GPU (a one-pair batch, which runs on the cluster-split kernel, where the timed batch ran it one CTA per pair)
+    #      and the SHA-256 of the denormalised vertices must equal the owner's ------------------------------------------
+    nxt_lo = shard_range(a.pairs, (rank + 1) % world, world)[0]
+    chk = engine.PairBatch([tuple(torch.from_numpy(x) for x in synth_pair(nxt_lo, a.verts, a.verts))], grid_resolution=a.grid, device=dev)
+    chk.deform(iters=a.iters, lr=1e-3)
+    re_hash = _sha(chk.finalize()[0])
+    chk.release()
+    if world > 1:
+        allh = [None] * world
+        dist.all_gather_object(allh, (first_hash, re_hash))
+    else:
+        allh = [(first_hash, re_hash)]
+    bad = [r for r in range(world) if allh[r][1] != allh[(r + 1) % world][0]]
+    parity = ("bit-identical: the first pair of every rank's block, recomputed on the previous rank's GPU by the "
+              "cluster-split kernel, has the same SHA-256 as the owner's result from the timed batch (%d of %d)" %
+              (world - len(bad), world)) if not bad else "MISMATCH on ranks %s" % bad
 
     line = None
     if rank == 0:
@@ -309,7 +543,8 @@ def run_b200(a):
         # DRAM traffic of this kernel per pair-iteration from the committed ncu --set full capture
         # (profiles/r01_deform_v7.txt: 148 pairs x 300 iterations, dram read 2.950 GB + write 0.739 GB)
         ncu_bytes_per_pair_iter = (2.950440e9 + 0.739227e9) / (148 * 300)
-        roof = {"kernel": "k_deform_adam_fused (one launch per step and rank: %d pairs x %d iterations)" % (n, a.iters),
+        roof = {"kernel": "k_deform_adam_fused (+ k_deform_adam_cluster for the partial wave); rank 0: %d pairs x %d "
+                          "iterations per step" % (n, a.iters),
                 "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "traffic": ncu_bytes_per_pair_iter * n * a.iters,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu capture (148 pairs x 300 iterations, "
@@ -322,61 +557,38 @@ def run_b200(a):
                         "neighbour gather; DRAM traffic is 7%% of the algorithmic bytes) and the fraction can exceed 1" %
                         (pair_iter_bytes(nV, nE) / 1e6)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config_of(a), "clocks": clk,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_of(a, world), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": int(launches), "roofline": roof}
+                "gpu_launches": int(launches), "roofline": roof, "multi_gpu_parity": parity}
 
     # ---- secondary metric: 128^3 distance-field build on a 50 000-triangle target (cfg3) -------------------
     if rank == 0 and not a.no_sdf128:
-        V, F = synth_mesh(25002, 1)
-        tV, tF = torch.from_numpy(V).to(dev), torch.from_numpy(F).to(dev)
-        sink = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
-        s = torch.cuda.current_stream().cuda_stream
-        # FP32 denominator: FFMA chain, 8 CTAs of 256 threads per SM
-        it_f = 20000
-        for _ in range(2):
-            capi.check(capi.lib().mo_microbench_fp32(148 * 8, 256, it_f, sink.data_ptr(), s))
-        f0, f1 = ev(), ev()
-        f0.record()
-        capi.check(capi.lib().mo_microbench_fp32(148 * 8, 256, it_f, sink.data_ptr(), s))
-        f1.record()
-        torch.cuda.synchronize()
-        fp32_tf = 148 * 8 * 256 * it_f * 8 * 2 / (f0.elapsed_time(f1) * 1e-3) / 1e12
-        times, stats = [], None
-        for k in range(3 + 5):
-            b0, b1 = ev(), ev()
-            b0.record()
-            pid = pd.InitializeDeformTemplate(tV, tF, 0, 128)
-            b1.record()
-            torch.cuda.synchronize()
-            if k >= 3:
-                times.append(b0.elapsed_time(b1))
-            stats = capi.template_build_stats(pid)
-            pd.DestroyTemplate(pid)
-        ms = float(np.mean(times))
-        flop = stats["fp32_tests"] * FLOP_PER_TEST + (stats["cull_tests"] + stats["disc_tests"]) * FLOP_PER_BOUND_TEST
-        tf = flop / (ms * 1e-3) / 1e12
-        line["sdf_build_128"] = {
-            "metric": "grid-SDF build ms at 128^3", "value": ms, "unit": "ms", "target_triangles": int(F.shape[0]),
-            "fp32_tests": stats["fp32_tests"], "cluster_tests": stats["cull_tests"], "disc_tests": stats["disc_tests"],
-            "fp64_tests": stats["fp64_tests"],
-            "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": tf / fp32_tf,
-                         "traffic": None,
-                         "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 "
-                                        "entry); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-                         "note": "achieved = (point-triangle tests executed x 74 + bounding-cylinder tests of clusters and "
-                                 "bounding-disc pre-tests of triangles x 38 FLOP, all counted by the kernel) / build time "
-                                 "including binning; the build is fast because it avoids the brute-force tests (N^3*M*74 = "
-                                 "%.3g FLOP), not because it saturates the FMA pipe: ncu issue slots 62%% busy, FMA pipe 26%%, "
-                                 "ALU 26%%, FP64 9%% (profiles/r01_sdf128_v4.txt)" % (128 ** 3 * F.shape[0] * 74.0)}}
+        blk, fp32_tf = sdf128_block(a, dev, ev, with_cpu=(world == 1 and not a.no_cpu))
+        line["sdf_build_128"] = blk
         line["fp32_tflops_measured"] = fp32_tf
+    if rank == 0 and not a.no_percall:
+        line["per_call_path"] = percall_block(a, dev, ev)
+
+    # ---- cfg5: one 256^3 field z-sharded over the ranks ------------------------------------------------------
+    if world > 1 and not a.no_slab:
+        blk = slab_block(a, dev, ev, rank, world, barrier)
+        if rank == 0:
+            line["sdf_build_256_slab"] = blk
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------
     if rank == 0 and world == 1 and not a.no_cpu:
-        v, desc, cores = cpu_sample(a, a.cpu_budget)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        v, desc, cores, first = cpu_sample(a, a.cpu_budget)
+        # the same sample is the parity check of this run: pair 0 through the same number of iterations on the GPU
+        chk = engine.PairBatch([tuple(torch.from_numpy(x) for x in synth_pair(first["pair"], a.verts, a.verts))],
+                               grid_resolution=a.grid, device=dev)
+        chk.deform(iters=first["iters"], lr=1e-3)
+        same = np.array_equal(chk.finalize()[0].cpu().numpy(), first["V"])
+        chk.release()
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                                "parity": ("GPU result of pair %d after the sample's %d iterations is bit-identical to the CPU's"
+                                           if same else "MISMATCH on pair %d after %d iterations") % (first["pair"], first["iters"])}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

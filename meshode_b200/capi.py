@@ -14,6 +14,7 @@ MO_OK = 0
 EDGES_RIGID, EDGES_GRAPH, EDGES_CAD = 0, 1, 2
 CERES_EDGE, CERES_ADAPTIVE_EDGE, CERES_ROT_EDGE = 0, 1, 2
 DEFORM_EXACT, DEFORM_CTA_ONLY, DEFORM_CLUSTER_ONLY = 1, 2, 4
+LAYER_SLICES = 4   # MO_LAYER_SLICES: voxel slices per z-tile layer of the cyclic sharded build
 
 _vp, _i, _d, _f = C.c_void_p, C.c_int, C.c_double, C.c_float
 _ip, _dp, _ullp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)

@@ -108,8 +108,11 @@ class PairBatch:
         return self.V
 
     def release(self):
-        for pid in self.pids:
-            pd.DestroyTemplate(pid)
+        """Returns the templates' buffers to the pool in the order of the current stream (the one deform() and
+        finalize() were enqueued on)."""
+        with torch.cuda.device(self.device):
+            for pid in self.pids:
+                pd.DestroyTemplate(pid)
         self.pids = []
 
 

@@ -71,7 +71,12 @@ def gather_pair_vertices(local_V, n_pairs, group=None, dst=0):
         raise ValueError("rank %d owns %d pairs, got %d results" % (rank, hi - lo, len(local_V)))
     if world == 1:
         return list(local_V)
-    dev = local_V[0].device if local_V else torch.device("cpu")
+    if local_V:
+        dev = local_V[0].device
+    elif dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())   # a rank that owns no pair still joins the NCCL collective
+    else:
+        dev = torch.device("cpu")
     counts = torch.tensor([v.shape[0] for v in local_V], dtype=torch.int64, device=dev)
     per = max(shard_range(n_pairs, r, world)[1] - shard_range(n_pairs, r, world)[0] for r in range(world))
     cnt_pad = torch.zeros(per, dtype=torch.int64, device=dev)
@@ -99,29 +104,103 @@ def gather_pair_vertices(local_V, n_pairs, group=None, dst=0):
     return out
 
 
-def build_template_sharded(tarV, tarF, grid_resolution, group=None):
-    """InitializeDeformTemplate with the grid build z-slab sharded over the ranks of ``group``:
-    every rank builds its slices on its own GPU, one all-gather (NCCL) assembles the fields, and
-    every rank ends up with a complete template.  Returns param_id."""
+def layer_groups(N, world, layer=4):
+    """Cyclic sharding of an N^3 field over ``world`` ranks by z-tile layers of ``layer`` slices: rank r builds layers
+    r, r + world, ...  Returns the number of groups (a group = ``world`` consecutive layers = ``layer*world`` slices,
+    contiguous in memory with rank r's piece at offset ``layer*r``) or 0 when N is not a multiple of ``layer*world``."""
+    span = layer * world
+    return N // span if N % span == 0 else 0
+
+
+def _check_collectively(ok, message, group=None):
+    """Raises on EVERY rank if any rank saw a problem (a one-sided raise would leave the others in a collective)."""
+    rank, world = _world(group)
+    if world > 1:
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok), group=group)
+        ok = all(flags)
+    if not ok:
+        raise ValueError(message)
+
+
+def build_template_sharded(tarV, tarF, grid_resolution, group=None, mode="auto", timings=False):
+    """InitializeDeformTemplate with the grid build sharded over the ranks of ``group``: every rank builds its share
+    of the voxel slices on its own GPU, all-gathers assemble the fields, and every rank ends up with a complete
+    template.  Returns param_id (and a dict of CUDA-event timings when ``timings``).
+
+    ``mode``: "cyclic" -- rank r builds z-tile layers r, r+world, ... (4 slices each), so every share spans the whole z
+    range and costs the same wherever the surface lies; one in-place all-gather per group of ``world`` layers and
+    field.  "slab" -- contiguous z-slabs (slices [r*N/world, (r+1)*N/world)), one all-gather per field; slabs through
+    the middle of a shape cost more than polar ones.  "auto" -- cyclic when N is a multiple of 4*world and the backend
+    is NCCL, else slab."""
     from . import capi
     from . import pyDeform as pd
     rank, world = _world(group)
     N = int(grid_resolution)
+    ev = (lambda: torch.cuda.Event(enable_timing=True)) if timings else None
     if world == 1:
-        return pd.InitializeDeformTemplate(tarV, tarF, 0, N)
-    z0, z1 = slab_range(N, rank, world)
+        e0, e1 = (ev(), ev()) if timings else (None, None)
+        if timings:
+            e0.record()
+        pid = pd.InitializeDeformTemplate(tarV, tarF, 0, N)
+        if timings:
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            return pid, {"mode": "single", "build_ms": ms, "gather_ms": 0.0, "total_ms": ms}
+        return pid
+    _check_collectively(world <= N, "more ranks (%d) than voxel slices (%d)" % (world, N), group)
+    nccl = dist.get_backend(group) == "nccl"
+    groups = layer_groups(N, world, capi.LAYER_SLICES)
+    if mode == "auto":
+        mode = "cyclic" if (groups > 0 and nccl) else "slab"
+    _check_collectively(mode in ("cyclic", "slab") and (mode != "cyclic" or (groups > 0 and nccl)),
+                        "cyclic sharding needs NCCL and grid_resolution %% (%d * world) == 0" % capi.LAYER_SLICES, group)
     V = tarV.cuda() if not tarV.is_cuda else tarV
     F = tarF.cuda() if not tarF.is_cuda else tarF
     s = torch.cuda.current_stream().cuda_stream
-    pid = capi.template_create_slab(V.data_ptr(), V.shape[0], F.data_ptr(), F.shape[0], N, z0, z1, s)
-    if N % world == 0 and dist.get_backend(group) == "nccl":
-        # equal slabs: all-gather IN PLACE on the template's own fields (rank r's slab already sits at offset r)
-        for field in pd.GridViews(pid):
-            dist.all_gather_into_tensor(field, field[z0:z1], group=group)
-        return pid
-    g64, g32, idx = pd.GetGrid(pid, z0, z1)
-    full64 = allgather_slabs(g64[z0:z1], N, group)
-    full32 = allgather_slabs(g32[z0:z1], N, group)
-    fulli = allgather_slabs(idx[z0:z1], N, group)
-    pd.SetGrid(pid, full64.contiguous(), full32.contiguous(), fulli.contiguous())
+    e0, e1, e2 = (ev(), ev(), ev()) if timings else (None, None, None)
+    if timings:
+        e0.record()
+    if mode == "cyclic":
+        pid = capi.template_create_layers(V.data_ptr(), V.shape[0], F.data_ptr(), F.shape[0], N, rank, world, s)
+        if timings:
+            e1.record()
+        span, L = capi.LAYER_SLICES * world, capi.LAYER_SLICES
+        fields = pd.GridViews(pid)
+        # all-gathers IN PLACE on the template's own fields; grouped so that NCCL issues them as one batch
+        try:
+            ctx = dist._coalescing_manager(group=group, device=V.device, async_ops=False)
+        except (AttributeError, TypeError):
+            ctx = None
+        def issue():
+            for field in fields:
+                for j in range(groups):
+                    chunk = field[j * span:(j + 1) * span]
+                    dist.all_gather_into_tensor(chunk, chunk[rank * L:(rank + 1) * L], group=group)
+        if ctx is not None:
+            with ctx:
+                issue()
+        else:
+            issue()
+    else:
+        z0, z1 = slab_range(N, rank, world)
+        pid = capi.template_create_slab(V.data_ptr(), V.shape[0], F.data_ptr(), F.shape[0], N, z0, z1, s)
+        if timings:
+            e1.record()
+        if N % world == 0 and nccl:
+            # equal slabs: all-gather IN PLACE on the template's own fields (rank r's slab already sits at offset r)
+            for field in pd.GridViews(pid):
+                dist.all_gather_into_tensor(field, field[z0:z1], group=group)
+        else:
+            g64, g32, idx = pd.GetGrid(pid, z0, z1)
+            full64 = allgather_slabs(g64[z0:z1], N, group)
+            full32 = allgather_slabs(g32[z0:z1], N, group)
+            fulli = allgather_slabs(idx[z0:z1], N, group)
+            pd.SetGrid(pid, full64.contiguous(), full32.contiguous(), fulli.contiguous())
+    if timings:
+        e2.record()
+        torch.cuda.synchronize()
+        return pid, {"mode": mode, "build_ms": e0.elapsed_time(e1), "gather_ms": e1.elapsed_time(e2),
+                     "total_ms": e0.elapsed_time(e2)}
     return pid

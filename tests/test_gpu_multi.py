@@ -36,16 +36,16 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         # ---- z-slab sharded build of one grid: equal slabs (in-place all-gather on the template's own fields)
-        #      and ragged slabs (N = 51: padded all-gather) -------------------------------------------------
+        #      ragged slabs (N = 51: padded all-gather) and cyclic layers (N = 48) ----------------------------
         V, F = synth_mesh(3000, 11)
         tV, tF = torch.from_numpy(V).to(dev), torch.from_numpy(F).to(dev)
-        for N in (51, 50):
+        for N in (51, 48, 50):   # ragged slabs (padded all-gather), cyclic z-tile layers (48 = 4 * world * 6), equal slabs
             pid = sharding.build_template_sharded(tV, tF, N)
             g64, g32, idx = pd.GetGrid(pid)
             ref = pd.InitializeDeformTemplate(tV, tF, 0, N)
             r64, r32, ridx = pd.GetGrid(ref)
             assert torch.equal(g64, r64) and torch.equal(g32, r32) and torch.equal(idx, ridx), N
-            if N == 51:
+            if N != 50:
                 pd.DestroyTemplate(pid); pd.DestroyTemplate(ref)
         # the assembled template serves lookups everywhere (a vertex needs slices z and z+1)
         P = torch.rand((4000, 3), device=dev)

@@ -51,6 +51,35 @@ def _worker(rank, world, port, N, n_pairs, out_dir):
                 assert v.shape == (5 + (i % 4), 3) and torch.equal(v, torch.full((5 + (i % 4), 3), float(i)) + torch.arange(3))
         else:
             assert allv is None
+        # cyclic z-tile layers: rank r owns layers r, r+world, ...; one in-place all-gather per group of `world` layers
+        # assembles the field (the same indexing build_template_sharded runs over NCCL on the template's own buffers)
+        L = 4
+        M = 4 * L * world
+        groups = S.layer_groups(M, world, L)
+        assert groups == 4 and S.layer_groups(M + L, world, L) == 0
+        fullM = torch.from_numpy(_field(M))
+        mine = torch.full((M, M, M), -1.0, dtype=torch.float64)
+        for layer in range(rank, M // L, world):
+            mine[layer * L:(layer + 1) * L] = fullM[layer * L:(layer + 1) * L]
+        span = L * world
+        for j in range(groups):
+            chunk = mine[j * span:(j + 1) * span]
+            parts = [torch.empty_like(chunk[:L]) for _ in range(world)]
+            dist.all_gather(parts, chunk[rank * L:(rank + 1) * L].contiguous())
+            chunk.copy_(torch.cat(parts, dim=0))
+        assert torch.equal(mine, fullM)
+        # a problem seen by ONE rank raises on every rank instead of leaving the others inside a collective
+        try:
+            S._check_collectively(rank != 1, "rank 1 is unhappy")
+            raised = False
+        except ValueError:
+            raised = True
+        assert raised
+        # a rank that owns no pair still takes part in the final gather
+        lo1, hi1 = S.shard_range(1, rank, world)
+        one = S.gather_pair_vertices([torch.ones((4, 3))] * (hi1 - lo1), 1)
+        if rank == 0:
+            assert len(one) == 1 and torch.equal(one[0], torch.ones((4, 3)))
         # max-over-ranks timing reduction used by bench.py
         t = torch.tensor([10.0 + rank], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
