@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmeshode_b200.so")
+# MESHODE_B200_LIB: another build of the same library (A/B timing of kernel variants inside one GPU session)
+LIB_PATH = os.environ.get("MESHODE_B200_LIB") or os.path.join(_HERE, "libmeshode_b200.so")
 
 MO_OK = 0
 EDGES_RIGID, EDGES_GRAPH, EDGES_CAD = 0, 1, 2

@@ -99,7 +99,7 @@ int allocate(Template& T, cudaStream_t s) {
   MO_CUDA(dev_alloc(&T.d_grid32, nvox, s));
   MO_CUDA(dev_alloc(&T.d_nearest, nvox, s));
   MO_CUDA(dev_alloc(&T.d_xf, 4, s));
-  MO_CUDA(dev_alloc(&T.d_stats, 8, s));
+  MO_CUDA(dev_alloc(&T.d_stats, 8 * (size_t)kStatSlots, s));
   return MO_OK;
 }
 
@@ -273,9 +273,12 @@ int mo_template_build_stats(int param_id, mo_stream_t stream, unsigned long long
                             unsigned long long* cull_tests, unsigned long long* disc_tests) {
   const TemplateRef T = lookup(param_id);
   if (!T) return MO_ERR_BAD_HANDLE;
-  unsigned long long h[8];
-  MO_CUDA(cudaMemcpyAsync(h, T->d_stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  unsigned long long all[8 * kStatSlots], h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  MO_CUDA(cudaMemcpyAsync(all, T->d_stats, sizeof(all), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   MO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int sl = 0; sl < kStatSlots; ++sl)
+    for (int k = 0; k < 8; ++k) h[k] += all[8 * sl + k];
+  h[3] = all[3];   // error bits live in slot 0
   if (fp32_tests) *fp32_tests = h[0];
   if (fp64_tests) *fp64_tests = h[1];
   if (cull_tests) *cull_tests = h[2];

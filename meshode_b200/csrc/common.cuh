@@ -12,6 +12,8 @@
 
 namespace mo {
 
+constexpr int kStatSlots = 32;   // the build kernel spreads its counters over this many slots of Template::d_stats
+
 // What DeformParams holds in the reference (src/interface/deform_params.h:7-25), as device buffers.
 struct Template {
   int device = 0;
@@ -25,7 +27,7 @@ struct Template {
   float* d_grid32 = nullptr;    // [N^3] (float) of the above
   int* d_nearest = nullptr;     // [N^3] nearest triangle (igl's I)
   double* d_xf = nullptr;       // [4] scale, trans.x, trans.y, trans.z  (params.scale / params.trans)
-  unsigned long long* d_stats = nullptr;   // [5] fp32 tests, fp64 tests, cull tests, error bits, sphere pre-tests
+  unsigned long long* d_stats = nullptr;   // [kStatSlots][8]: fp32 tests, fp64 tests, cull tests, error bits (slot 0 only), disc pre-tests; counters summed over the slots
   // one edge set per template (params.edge_offset / edge_lambda)
   int kind = MO_EDGES_NONE;
   int eV = 0, eF = 0, eE = 0, nEdges = 0;

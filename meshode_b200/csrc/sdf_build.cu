@@ -40,10 +40,10 @@ constexpr int kCellVox = 4;       // voxels per cluster-cell edge
 constexpr int kCoarse = 4;        // cluster cells per coarse-cell edge
 constexpr int kWarps = kTile * kTile * kTileZ / 32;
 constexpr int kThreads = kWarps * 32;
-constexpr int kCtasPerSm = 3;
-constexpr int kCoarseChunk = 32;                              // coarse cells expanded per pass
-constexpr int kListMax = kCoarseChunk * kCoarse * kCoarse * kCoarse;   // clusters listed per pass
-constexpr int kMaxCoarse = 1024;  // coarse cells collected per enumeration chunk
+#ifndef MO_SDF_CTAS
+#define MO_SDF_CTAS 3
+#endif
+constexpr int kCtasPerSm = MO_SDF_CTAS;
 constexpr int kQueueCap = 8;      // per-lane queue of FP64 candidates
 constexpr int kRecParts = 6;      // float4 per triangle record: 4 for the distance test, 2 for the disc bound
 
@@ -54,14 +54,16 @@ constexpr float kErrA = 1.2e-5f;
 constexpr float kErrB = 1.2e-9f;
 
 struct SdfArgs {
-  int N, nc, ncc, ntile, tz0, tz_stride, z0, z1;   // tile layers tz0, tz0 + tz_stride, ... ; voxel slices [z0, z1) are stored
+  int N, nc, ncc, nsc, ntile, tz0, tz_stride, z0, z1;   // tile layers tz0, tz0 + tz_stride, ... ; voxel slices [z0, z1) are stored
   float ccs;                      // coarse cell size in normalised units
   const unsigned* max_ext;        // bit pattern of the largest triangle AABB extent
-  const int* coarse_cnt;          // [ncoarse] triangles binned into the coarse cell
-  const unsigned* coarse_bb;      // [ncoarse*6] ordered-uint lo xyz, hi xyz of those triangles
-  const int2* cl_sc;              // [ncell] (first record, count) of the cell's triangles
-  const float4* cl_c;             // [ncell] cluster centre, cylinder radius
-  const float4* cl_n;             // [ncell] cluster axis (unit), cylinder half height
+  const int* coarse_ncl;          // [ncoarse] non-empty clusters of the coarse cell: packed at [64*C, 64*C + ncl)
+  const unsigned* coarse_bb;      // [ncoarse*6] ordered-uint lo xyz, hi xyz of the triangles binned into the coarse cell
+  const int2* pk_sc;              // [ncell] packed: (first record, count) of the cluster's triangles
+  const float4* cl_c;             // [ncell] packed: cluster centre, cylinder radius
+  const float4* cl_n;             // [ncell] packed: cluster axis (unit), cylinder half height
+  const int* super_cnt;           // [nsc^3] non-empty coarse cells of the super cell (4^3 coarse cells)
+  const unsigned* super_bb;       // [nsc^3*6] AABB of the triangles binned into the super cell
   const float4* rec;              // [nF*6] cell-sorted FP32 records (4 distance + 2 disc)
   const double* rec64;            // [nF*9] cell-sorted FP64 vertices
   const int* tri_id;              // [nF] cell-sorted -> original triangle index
@@ -281,12 +283,21 @@ __device__ __forceinline__ double warp_max_d(double v) {
 
 // one warp per cell: bounding cylinder of the cell's triangles about their mean centroid, axis = area-weighted
 // mean normal (any axis gives a valid bound; this one makes it flat for a smooth patch)
+// The non-empty clusters of a coarse cell are PACKED at the front of its 64 slots (slot = rank of the cell among the
+// coarse cell's non-empty cells), so the search kernel walks ceil(ncl/32) batches instead of two half-empty ones.
 __global__ void k_cluster(const int2* __restrict__ cl_sc, int ncell, const double* __restrict__ rec64,
-                          float4* __restrict__ cl_c, float4* __restrict__ cl_n) {
+                          float4* __restrict__ cl_c, float4* __restrict__ cl_n, int2* __restrict__ pk_sc,
+                          int* __restrict__ coarse_ncl) {
   const int cell = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (cell >= ncell) return;
+  const int coarse = cell >> 6, local = cell & 63;
+  const unsigned lo_mask = __ballot_sync(0xffffffffu, cl_sc[coarse * 64 + lane].y > 0);
+  const unsigned hi_mask = __ballot_sync(0xffffffffu, cl_sc[coarse * 64 + 32 + lane].y > 0);
+  if (local == 0 && lane == 0) coarse_ncl[coarse] = __popc(lo_mask) + __popc(hi_mask);
   const int2 sc = cl_sc[cell];
   if (sc.y == 0) return;
+  const int slot = coarse * 64 + (local < 32 ? __popc(lo_mask & ((1u << local) - 1u))
+                                             : __popc(lo_mask) + __popc(hi_mask & ((1u << (local - 32)) - 1u)));
   double sn[3] = {0.0, 0.0, 0.0}, sm[3] = {0.0, 0.0, 0.0};
   for (int i = lane; i < sc.y; i += 32) {
     const double* tv = rec64 + 9 * (size_t)(sc.x + i);
@@ -312,8 +323,40 @@ __global__ void k_cluster(const int2* __restrict__ cl_sc, int ncell, const doubl
   }
   mh = warp_max_d(mh); mt2 = warp_max_d(mt2);
   if (lane == 0) {
-    cl_c[cell] = make_float4(cf[0], cf[1], cf[2], pad_rho(mt2));
-    cl_n[cell] = make_float4(nf[0], nf[1], nf[2], pad_tau(mh));
+    cl_c[slot] = make_float4(cf[0], cf[1], cf[2], pad_rho(mt2));
+    cl_n[slot] = make_float4(nf[0], nf[1], nf[2], pad_tau(mh));
+    pk_sc[slot] = sc;
+  }
+}
+
+// one warp per super cell (4^3 coarse cells): number of non-empty coarse cells and the union of their AABBs
+__global__ void k_super(const int* __restrict__ coarse_ncl, const unsigned* __restrict__ coarse_bb, int ncc, int nsc,
+                        int* __restrict__ super_cnt, unsigned* __restrict__ super_bb) {
+  const int S = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (S >= nsc * nsc * nsc) return;
+  const int sx = S % nsc, sy = (S / nsc) % nsc, sz = S / (nsc * nsc);
+  unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  int cnt = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int l = 32 * h + lane;
+    const int cx = 4 * sx + (l & 3), cy = 4 * sy + ((l >> 2) & 3), cz = 4 * sz + (l >> 4);
+    if (cx < ncc && cy < ncc && cz < ncc) {
+      const int c = (cz * ncc + cy) * ncc + cx;
+      if (coarse_ncl[c] > 0) {
+        ++cnt;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { lo[j] = min(lo[j], coarse_bb[6 * (size_t)c + j]); hi[j] = max(hi[j], coarse_bb[6 * (size_t)c + 3 + j]); }
+      }
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { lo[j] = __reduce_min_sync(0xffffffffu, lo[j]); hi[j] = __reduce_max_sync(0xffffffffu, hi[j]); }
+  if (lane == 0) {
+    super_cnt[S] = cnt;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { super_bb[6 * (size_t)S + j] = lo[j]; super_bb[6 * (size_t)S + 3 + j] = hi[j]; }
   }
 }
 
@@ -478,38 +521,62 @@ struct LaneState {
   unsigned n64;
 };
 
-__device__ __forceinline__ void flush_queue(LaneState& st, const int* s_lid, const float* s_lq, const int tid,
-                                            const SdfArgs& A, const double px, const double py, const double pz) {
-  for (int k = 0; k < st.cnt; ++k) {
-    if (s_lq[k * kThreads + tid] <= st.ub) {
-      const int gi = s_lid[k * kThreads + tid];
-      const double d = tri_exact64(A.rec64 + 9 * (size_t)gi, px, py, pz);
-      const int id = A.tri_id[gi];
-      st.n64++;
-      if (d < st.best64 || (d == st.best64 && id < st.best_id)) { st.best64 = d; st.best_id = id; }
-    }
-  }
-  st.cnt = 0;
-  if (st.best_id >= 0) st.ub = fminf(st.ub, __double2float_ru(st.best64));
-}
-
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
-// per-lane view of the kernel state that the cluster routine needs
+// per-lane view of the warp's state that the cluster routine needs.  Every warp owns a private slice of the CTA's
+// shared memory and never synchronises with the other warps of its CTA.
 struct WarpCtx {
-  float4* s_tri;      // this warp's staging buffer [kRecParts][32]
-  const int* s_lid;
-  float* s_lq;
-  int* s_lidw;
-  int tid, lane;
+  float4* s_tri;      // [kRecParts][32] staged triangle records
+  int* s_lid;         // [kQueueCap][32] queued FP64 candidates: record index
+  float* s_lq;        // [kQueueCap][32] their FP32 lower bounds
+  int lane;
   bool valid;
   float px, py, pz;
-  double pxd, pyd, pzd;
+  int vx, vy, vz, N;  // the query point is (vx/N, vy/N, vz/N) in FP64 (mesh.cc:115-117), formed when needed
 };
+
+// Exact FP64 evaluation of everything queued, CONVERGED over the warp: in round k every lane that still holds a k-th
+// candidate which can win evaluates it, so the (slow, branchy) FP64 routine runs with as many lanes as have work
+// instead of one lane at a time.  An entry is skipped when its FP32 lower bound exceeds the lane's upper bound: its
+// exact distance is then strictly larger than the running minimum, so it can neither win nor tie.
+__device__ __forceinline__ void warp_flush(const SdfArgs& A, const WarpCtx& w, LaneState& st) {
+  const int maxc = __reduce_max_sync(0xffffffffu, st.cnt);
+  if (maxc == 0) return;
+  const double pxd = __ddiv_rn((double)w.vx, (double)w.N), pyd = __ddiv_rn((double)w.vy, (double)w.N),
+               pzd = __ddiv_rn((double)w.vz, (double)w.N);
+  for (int k = 0; k < maxc; ++k) {
+    if (k < st.cnt && w.s_lq[k * 32 + w.lane] <= st.ub) {
+      const int gi = w.s_lid[k * 32 + w.lane];
+      const double d = tri_exact64(A.rec64 + 9 * (size_t)gi, pxd, pyd, pzd);
+      const int id = A.tri_id[gi];
+      st.n64++;
+      if (d < st.best64 || (d == st.best64 && id < st.best_id)) {
+        st.best64 = d; st.best_id = id;
+        st.ub = fminf(st.ub, __double2float_ru(d));
+      }
+    }
+  }
+  st.cnt = 0;
+}
+
+// Some lane's queue is full: first drop the entries that can no longer win (the upper bound has usually moved
+// below them since they were queued); only if a lane is still full, evaluate exactly.  Called by all 32 lanes.
+__device__ __forceinline__ void queue_make_room(const SdfArgs& A, const WarpCtx& w, LaneState& st) {
+  int n = 0;
+  for (int k = 0; k < st.cnt; ++k) {
+    const float lq = w.s_lq[k * 32 + w.lane];
+    if (lq <= st.ub) {
+      if (n != k) { w.s_lq[n * 32 + w.lane] = lq; w.s_lid[n * 32 + w.lane] = w.s_lid[k * 32 + w.lane]; }
+      ++n;
+    }
+  }
+  st.cnt = n;
+  if (__any_sync(0xffffffffu, st.cnt == kQueueCap)) warp_flush(A, w, st);
+}
 
 // One cluster against the warp's 32 voxels: per-voxel cylinder test, then the cluster's triangles are staged
 // 32 at a time in the warp's shared memory, pre-tested per voxel with their disc bound and evaluated in FP32
@@ -537,10 +604,11 @@ __device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx&
       float e;
       const float q = tri_q(w.s_tri[j], w.s_tri[32 + j], w.s_tri[64 + j], w.s_tri[96 + j], w.px, w.py, w.pz, e);
       const float qlo = q - e;
-      if (w.valid && qlo <= st.ub) {
-        if (st.cnt == kQueueCap) flush_queue(st, w.s_lid, w.s_lq, w.tid, A, w.pxd, w.pyd, w.pzd);
-        w.s_lidw[st.cnt * kThreads + w.tid] = sc.x + tb + j;
-        w.s_lq[st.cnt * kThreads + w.tid] = qlo;
+      const bool push = w.valid && qlo <= st.ub;
+      if (__any_sync(0xffffffffu, push && st.cnt == kQueueCap)) queue_make_room(A, w, st);
+      if (push && qlo <= st.ub) {
+        w.s_lid[st.cnt * 32 + w.lane] = sc.x + tb + j;
+        w.s_lq[st.cnt * 32 + w.lane] = qlo;
         st.cnt++;
       }
       st.ub = fminf(st.ub, q + e);
@@ -548,168 +616,152 @@ __device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx&
   }
 }
 
+// gap^2 between an AABB stored as ordered uints (lo xyz, hi xyz) and the block's sample box
+__device__ __forceinline__ float aabb_gap2(const unsigned* __restrict__ bb, const float blo[3], const float bhi[3]) {
+  float d2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float lo = o2f(__ldg(bb + j)), hi = o2f(__ldg(bb + 3 + j));
+    const float gap = fmaxf(0.f, fmaxf(lo - bhi[j], blo[j] - hi));
+    d2 = fmaf(gap, gap, d2);
+  }
+  return d2;
+}
+
+// The warp holds 64 candidate keys (gap^2 >= 0; two per lane: slot = lane, lane + 32).  Drops the keys above `bound`
+// (with the safety factor of the AABB tests), removes the smallest remaining key and returns its slot, -1 if none.
+__device__ __forceinline__ int take_nearest(float& k0, float& k1, const float bound, const int lane) {
+  const float kInf = __int_as_float(0x7f800000);
+  if (k0 * 0.9999f > bound) k0 = kInf;   // (inf > inf is false: without a bound every candidate stays)
+  if (k1 * 0.9999f > bound) k1 = kInf;
+  const unsigned bits = __float_as_uint(fminf(k0, k1));   // non-negative floats: the bit patterns are monotone
+  const unsigned mn = __reduce_min_sync(0xffffffffu, bits);
+  if (mn == 0x7f800000u) return -1;
+  const int src = __ffs(__ballot_sync(0xffffffffu, bits == mn)) - 1;
+  const int which = __shfl_sync(0xffffffffu, k0 <= k1 ? 0 : 1, src);
+  if (lane == src) { if (which == 0) k0 = kInf; else k1 = kInf; }
+  return src + 32 * which;
+}
+
+constexpr int kWarpSmem = kRecParts * 32 * 16 + kQueueCap * 32 * 8;   // bytes of shared memory per warp
+constexpr size_t kSdfSmem = (size_t)kWarps * kWarpSmem;
+
+// One warp per 4x4x2-voxel block, one lane per voxel; the eight warps of a CTA cover an 8x8x4 tile (neighbouring
+// blocks share cluster and record lines in L1) but are otherwise INDEPENDENT: no CTA barrier, no shared lists.  A warp
+// sweeps the coarse cells ring by ring around its block (lanes over coarse cells, AABB test against the block's sample
+// box with the block's largest running bound; the sweep stops when the ring's lower bound exceeds it), tests the
+// clusters of every surviving coarse cell against the block (lanes over clusters, ballot + compaction) and hands the
+// survivors to process_cluster (lanes over voxels).
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* s_tri = reinterpret_cast<float4*>(smem_raw);                   // [kWarps][kRecParts][32]
-  float4* s_wc = s_tri + kWarps * kRecParts * 32;                        // [kWarps][32] block survivors: centre, rho
-  float4* s_wn = s_wc + kWarps * 32;                                     // [kWarps][32] axis, tau
-  int2* s_wsc = reinterpret_cast<int2*>(s_wn + kWarps * 32);             // [kWarps][32] start, count
-  int* s_lid = reinterpret_cast<int*>(s_wsc + kWarps * 32);              // [kQueueCap][kThreads]
-  float* s_lq = reinterpret_cast<float*>(s_lid + kQueueCap * kThreads);  // [kQueueCap][kThreads]
-  int* s_list = reinterpret_cast<int*>(s_lq + kQueueCap * kThreads);     // [kListMax]
-  int* s_coarse = s_list + kListMax;                                     // [kMaxCoarse]
-  __shared__ int s_ncoarse, s_nlist;
-  __shared__ unsigned s_ub[2];
-  __shared__ unsigned long long s_stats[5];
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = A.N, ncc = A.ncc;
   const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile, tz = A.tz0 + (blockIdx.x / (A.ntile * A.ntile)) * A.tz_stride;   // tz in units of kTileZ
 
+  WarpCtx w;
+  {
+    unsigned char* base = smem_raw + (size_t)warp * kWarpSmem;
+    w.s_tri = reinterpret_cast<float4*>(base);
+    w.s_lid = reinterpret_cast<int*>(w.s_tri + kRecParts * 32);
+    w.s_lq = reinterpret_cast<float*>(w.s_lid + kQueueCap * 32);
+  }
   // this lane's voxel; the warp owns a 4x4x2 block of the tile
   const int bx = tx * kTile + (warp & 1) * 4, by = ty * kTile + ((warp >> 1) & 1) * 4, bz = tz * kTileZ + (warp >> 2) * 2;
   const int vx = bx + (lane & 3), vy = by + ((lane >> 2) & 3), vz = bz + (lane >> 4);
   const double invN = 1.0 / (double)N;
-  WarpCtx w;
-  w.s_tri = s_tri + warp * kRecParts * 32; w.s_lid = s_lid; w.s_lidw = s_lid; w.s_lq = s_lq; w.tid = tid; w.lane = lane;
+  w.lane = lane;
   w.valid = vx < N && vy < N && vz < N && vz >= A.z0 && vz < A.z1;
-  w.pxd = __ddiv_rn((double)vx, (double)N); w.pyd = __ddiv_rn((double)vy, (double)N);
-  w.pzd = __ddiv_rn((double)vz, (double)N);   // mesh.cc:115-117
-  w.px = (float)w.pxd; w.py = (float)w.pyd; w.pz = (float)w.pzd;
+  if (!__any_sync(0xffffffffu, w.valid)) return;   // the whole block lies outside the grid or the slab
+  w.vx = vx; w.vy = vy; w.vz = vz; w.N = N;
+  w.px = (float)__ddiv_rn((double)vx, (double)N); w.py = (float)__ddiv_rn((double)vy, (double)N);
+  w.pz = (float)__ddiv_rn((double)vz, (double)N);   // mesh.cc:115-117, rounded once to FP32 for the search
   const bool valid = w.valid;
-  // block and tile bounding spheres (sample points, unclipped)
+  // block bounding sphere (sample points, unclipped) and sample box (clipped to the grid and the slab)
   const float wcx = (float)((bx + 1.5) * invN), wcy = (float)((by + 1.5) * invN), wcz = (float)((bz + 0.5) * invN);
   const float Rw = (float)(2.1795 * invN * 1.0001);   // half diagonal of the 3x3x1-interval sample box
-  const float tcx = (float)((tx * kTile + 3.5) * invN), tcy = (float)((ty * kTile + 3.5) * invN), tcz = (float)((tz * kTileZ + 1.5) * invN);
-  const float Rt = (float)(5.1721 * invN * 1.0001);   // half diagonal of the 7x7x3-interval sample box
-  // tile sample box (clipped to the grid and the slab) for the coarse AABB test
-  const float tlo[3] = {(float)(tx * kTile * invN), (float)(ty * kTile * invN), (float)(max(tz * kTileZ, A.z0) * invN)};
-  const float thi[3] = {(float)(min(tx * kTile + kTile - 1, N - 1) * invN), (float)(min(ty * kTile + kTile - 1, N - 1) * invN),
-                        (float)(min(min(tz * kTileZ + kTileZ - 1, N - 1), A.z1 - 1) * invN)};
+  const float blo[3] = {(float)(bx * invN), (float)(by * invN), (float)(max(bz, A.z0) * invN)};
+  const float bhi[3] = {(float)(min(bx + 3, N - 1) * invN), (float)(min(by + 3, N - 1) * invN),
+                        (float)(min(min(bz + 1, N - 1), A.z1 - 1) * invN)};
 
   const float kInf = __int_as_float(0x7f800000);
   LaneState st;
   st.best64 = DBL_MAX; st.best_id = -1; st.ub = kInf; st.cnt = 0; st.n64 = 0;
   unsigned n32 = 0, n_cyl = 0, n_disc = 0;
-  float thr_w = kInf;     // (sqrt(max ub of the block) + Rw)^2
-  float ub_cta = kInf;    // max ub of the tile
-  float thr_t = kInf;     // (sqrt(ub_cta) + Rt)^2
-  const float max_ext = __uint_as_float(*A.max_ext);
-  if (tid < 5) s_stats[tid] = 0ull;
-  if (tid < 2) s_ub[tid] = 0u;
-  int par = 0;
+  float ubw = kInf;       // max ub over the block's voxels
+  float thr_w = kInf;     // (sqrt(ubw) + Rw)^2
 
-  const int Cx = tx >> 1, Cy = ty >> 1, Cz = tz >> 2;   // the tile's coarse cell (a tile is 2 x 2 x 1 cells)
-  for (int r = 0; r <= ncc; ++r) {
-    if (r >= 1) {
-      const float lb = (float)(r - 1) * A.ccs - max_ext;   // nothing binned in ring >= r is closer than this
-      if (lb > 0.f && lb * lb * 0.9999f > ub_cta) break;
-      const int q = r - 1;                                 // ring r-1 already enclosed the whole coarse grid
-      if (Cx - q <= 0 && Cy - q <= 0 && Cz - q <= 0 && Cx + q >= ncc - 1 && Cy + q >= ncc - 1 && Cz + q >= ncc - 1) break;
+  // ---- two-level sweep, nearest first: super cells (4^3 coarse cells) -> coarse cells -> clusters ---------------
+  // Every level holds its candidates in registers (two per lane for the 64 children of a node), takes the one with
+  // the smallest AABB gap to the block first and drops candidates whose gap exceeds the block's bound as it tightens.
+  const int nsc = A.nsc, nsup = nsc * nsc * nsc;
+  for (int sb = 0; sb < nsup; sb += 64) {
+    float sk[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int S = sb + 32 * h + lane;
+      sk[h] = kInf;
+      if (S < nsup && __ldg(&A.super_cnt[S]) > 0) sk[h] = aabb_gap2(A.super_bb + 6 * (size_t)S, blo, bhi);
     }
-    const int side = 1 + 2 * r;
-    const int x0 = Cx - r, y0 = Cy - r, z0c = Cz - r;
-    const int nenum = side * side * side;
-    for (int base = 0; base < nenum; base += kMaxCoarse) {
-      __syncthreads();
-      if (tid == 0) s_ncoarse = 0;
-      __syncthreads();
-      const int lim = min(nenum, base + kMaxCoarse);
-      for (int i = base + tid; i < lim; i += kThreads) {
-        const int ix = i % side, iy = (i / side) % side, iz = i / (side * side);
-        if (r > 0 && ix > 0 && ix < side - 1 && iy > 0 && iy < side - 1 && iz > 0 && iz < side - 1) continue;
-        const int cx = x0 + ix, cy = y0 + iy, cz = z0c + iz;
-        if ((unsigned)cx >= (unsigned)ncc || (unsigned)cy >= (unsigned)ncc || (unsigned)cz >= (unsigned)ncc) continue;
-        const int c = (cz * ncc + cy) * ncc + cx;
-        if (A.coarse_cnt[c] == 0) continue;
-        float d2 = 0.f;
+    for (;;) {
+      const int ss = take_nearest(sk[0], sk[1], ubw, lane);
+      if (ss < 0) break;
+      const int S = sb + ss;
+      const int sx = S % nsc, sy = (S / nsc) % nsc, sz = S / (nsc * nsc);
+      float ck[2];
+      int cidx[2];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float lo = o2f(A.coarse_bb[6 * (size_t)c + j]), hi = o2f(A.coarse_bb[6 * (size_t)c + 3 + j]);
-          const float gap = fmaxf(0.f, fmaxf(lo - thi[j], tlo[j] - hi));
-          d2 = fmaf(gap, gap, d2);
-        }
-        if (d2 * 0.9999f <= ub_cta) s_coarse[atomicAdd(&s_ncoarse, 1)] = c;
+      for (int h = 0; h < 2; ++h) {
+        const int l = 32 * h + lane;
+        const int cx = 4 * sx + (l & 3), cy = 4 * sy + ((l >> 2) & 3), cz = 4 * sz + (l >> 4);
+        ck[h] = kInf;
+        cidx[h] = (cz * ncc + cy) * ncc + cx;
+        if (cx < ncc && cy < ncc && cz < ncc && __ldg(&A.coarse_ncl[cidx[h]]) > 0)
+          ck[h] = aabb_gap2(A.coarse_bb + 6 * (size_t)cidx[h], blo, bhi);
       }
-      __syncthreads();
-      const int ncoarse = s_ncoarse;
-      for (int cb = 0; cb < ncoarse; cb += kCoarseChunk) {
-        // ---- clusters of up to kCoarseChunk coarse cells against the tile -------------------------
-        if (tid == 0) s_nlist = 0;
-        __syncthreads();
-        const int nexp = min(kCoarseChunk, ncoarse - cb) * 64;
-        for (int i = tid; i < nexp; i += kThreads) {
-          const int cell = s_coarse[cb + (i >> 6)] * 64 + (i & 63);
-          if (__ldg(&A.cl_sc[cell]).y == 0) continue;
-          n_cyl++;
-          if (!cyl_skip(tcx, tcy, tcz, thr_t, __ldg(&A.cl_c[cell]), __ldg(&A.cl_n[cell]))) s_list[atomicAdd(&s_nlist, 1)] = cell;
-        }
-        __syncthreads();
-        const int n = s_nlist;
-        if (n > 0) {
-          // ---- pass 1 (block without a bound yet): the cluster nearest to the block goes first ------
-          int first = -1;
-          if (thr_w == kInf) {
-            float bl = kInf;
-            for (int b = 0; b < n; b += 32) {
-              const int j = b + lane;
-              if (j < n) {
-                const int cell = s_list[j];
-                const float l = cyl_lb2(wcx, wcy, wcz, __ldg(&A.cl_c[cell]), __ldg(&A.cl_n[cell]));
-                if (l < bl) { bl = l; first = cell; }
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
-              const int oc = __shfl_xor_sync(0xffffffffu, first, o);
-              if (ol < bl || (ol == bl && oc > first)) { bl = ol; first = oc; }
-            }
-            n_cyl += (unsigned)((n + 31) >> 5);
-            if (first >= 0) {
-              process_cluster(A, w, st, __ldg(&A.cl_c[first]), __ldg(&A.cl_n[first]), __ldg(&A.cl_sc[first]), n_cyl, n_disc, n32);
-              const float su = sqrtf(warp_max(valid ? st.ub : 0.f)) + Rw;
+      for (;;) {
+        const int cs = take_nearest(ck[0], ck[1], ubw, lane);
+        if (cs < 0) break;
+        const int cc = __shfl_sync(0xffffffffu, cs >= 32 ? cidx[1] : cidx[0], cs & 31);
+        const int ncl = __ldg(&A.coarse_ncl[cc]);
+        // ---- the clusters of this coarse cell against the block: lanes over clusters, nearest first, every
+        //      survivor re-checked against the block's bound when it has tightened -----------------------------
+        for (int b = 0; b < ncl; b += 32) {
+          const int j = b + lane;
+          const bool has = j < ncl;
+          const int cell = cc * 64 + (has ? j : 0);
+          const float4 C = __ldg(&A.cl_c[cell]), Nm = __ldg(&A.cl_n[cell]);
+          const int2 sc = __ldg(&A.pk_sc[cell]);
+          unsigned key = has ? __float_as_uint(cyl_lb2(wcx, wcy, wcz, C, Nm)) : 0x7f800000u;   // ordering only (>= 0: bits are monotone)
+          n_cyl += has ? 2u : 0u;
+          bool recheck = true;
+          for (;;) {
+            if (recheck && key != 0x7f800000u && cyl_skip(wcx, wcy, wcz, thr_w, C, Nm)) key = 0x7f800000u;
+            const unsigned bk = __reduce_min_sync(0xffffffffu, key);
+            if (bk == 0x7f800000u) break;
+            const int who = __ffs(__ballot_sync(0xffffffffu, key == bk)) - 1;
+            const float4 fC = make_float4(__shfl_sync(0xffffffffu, C.x, who), __shfl_sync(0xffffffffu, C.y, who),
+                                          __shfl_sync(0xffffffffu, C.z, who), __shfl_sync(0xffffffffu, C.w, who));
+            const float4 fN = make_float4(__shfl_sync(0xffffffffu, Nm.x, who), __shfl_sync(0xffffffffu, Nm.y, who),
+                                          __shfl_sync(0xffffffffu, Nm.z, who), __shfl_sync(0xffffffffu, Nm.w, who));
+            const int2 fsc = make_int2(__shfl_sync(0xffffffffu, sc.x, who), __shfl_sync(0xffffffffu, sc.y, who));
+            if (lane == who) key = 0x7f800000u;
+            process_cluster(A, w, st, fC, fN, fsc, n_cyl, n_disc, n32);
+            const float nub = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(st.ub) : 0u));
+            recheck = nub < ubw;
+            if (recheck) {
+              ubw = nub;
+              const float su = sqrtf(ubw) + Rw;
               thr_w = su * su * 1.00001f;
             }
           }
-          // ---- pass 2: lanes over clusters against the block, survivors against every voxel ---------
-          for (int b = 0; b < n; b += 32) {
-            const int j = b + lane;
-            const bool has = j < n;
-            const int cell = s_list[has ? j : 0];
-            const float4 C = __ldg(&A.cl_c[cell]), Nm = __ldg(&A.cl_n[cell]);
-            const bool keep = has && cell != first && !cyl_skip(wcx, wcy, wcz, thr_w, C, Nm);
-            n_cyl += has ? 1u : 0u;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m == 0u) continue;
-            __syncwarp();
-            if (keep) {
-              const int pos = __popc(m & ((1u << lane) - 1u));
-              s_wc[warp * 32 + pos] = C; s_wn[warp * 32 + pos] = Nm; s_wsc[warp * 32 + pos] = __ldg(&A.cl_sc[cell]);
-            }
-            __syncwarp();
-            const int np = __popc(m);
-            for (int k = 0; k < np; ++k)
-              process_cluster(A, w, st, s_wc[warp * 32 + k], s_wn[warp * 32 + k], s_wsc[warp * 32 + k], n_cyl, n_disc, n32);
-            const float su = sqrtf(warp_max(valid ? st.ub : 0.f)) + Rw;
-            thr_w = su * su * 1.00001f;
-          }
         }
-        const float um = warp_max(valid ? st.ub : 0.f);
-        if (lane == 0) atomicMax(&s_ub[par], __float_as_uint(um));
-        __syncthreads();
-        ub_cta = __uint_as_float(s_ub[par]);
-        par ^= 1;
-        if (tid == 0) s_ub[par] = 0u;   // next pass's slot; not touched again before two more barriers
-        const float st_ = sqrtf(ub_cta) + Rt;
-        thr_t = st_ * st_ * 1.00001f;
       }
     }
   }
 
   // ---- exact FP64 evaluation of everything still queued, then store ------------------
+  warp_flush(A, w, st);
   if (valid) {
-    flush_queue(st, s_lid, s_lq, tid, A, w.pxd, w.pyd, w.pzd);
     const size_t o = ((size_t)vz * N + vy) * N + vx;
     const double d = st.best_id >= 0 ? __dsqrt_rn(st.best64) : 1e30;   // mesh.cc:146
     A.grid64[o] = d;
@@ -723,40 +775,42 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
     ac += __shfl_xor_sync(0xffffffffu, ac, o);
     as += __shfl_xor_sync(0xffffffffu, as, o);
   }
-  if (lane == 0) { atomicAdd(&s_stats[0], a32); atomicAdd(&s_stats[1], a64); atomicAdd(&s_stats[2], ac); atomicAdd(&s_stats[3], as); }
-  __syncthreads();
-  if (tid < 3) atomicAdd(&A.stats[tid], s_stats[tid]);
-  if (tid == 3) atomicAdd(&A.stats[4], s_stats[3]);
+  if (lane == 0) {
+    unsigned long long* slot = A.stats + 8 * ((blockIdx.x * kWarps + warp) % kStatSlots);
+    atomicAdd(slot + 0, a32); atomicAdd(slot + 1, a64); atomicAdd(slot + 2, ac); atomicAdd(slot + 4, as);
+  }
 }
-
-constexpr size_t kSdfSmem = (size_t)kWarps * kRecParts * 32 * 16 + (size_t)kWarps * 32 * (16 + 16 + 8) +
-                            (size_t)kQueueCap * kThreads * 8 + (size_t)kListMax * 4 + (size_t)kMaxCoarse * 4;
 
 int run_build(Template& T, cudaStream_t s) {
   const int N = T.N, nF = T.nF, nV = T.nV;
   const int ntile = div_up(N, kTile), nc = 2 * ntile, ncc = div_up(nc, kCoarse);
-  const size_t ncoarse = (size_t)ncc * ncc * ncc, ncell = ncoarse * 64;
+  const int nsc = div_up(ncc, 4);
+  const size_t ncoarse = (size_t)ncc * ncc * ncc, ncell = ncoarse * 64, nsuper = (size_t)nsc * nsc * nsc;
   const size_t nvox = (size_t)N * N * N;
 
   // one scratch allocation, stream ordered
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t b_count = (2 * ncell + ncoarse) * sizeof(int);   // cell count + cell fill + coarse count (zeroed together)
+  const size_t b_count = (2 * ncell + 2 * ncoarse) * sizeof(int);   // cell count + cell fill + coarse count + coarse clusters (zeroed together)
   const size_t b_sc = ncell * sizeof(int2);
   const size_t b_cl = ncell * sizeof(float4);
   const size_t b_bb = 6 * ncoarse * sizeof(unsigned);
+  const size_t b_sup = 7 * nsuper * sizeof(unsigned);            // super-cell AABBs + counts
   const size_t b_tri = 2 * (size_t)nF * sizeof(int);            // tri_cell + tri_id
   const size_t b_rec = (size_t)nF * kRecParts * 16, b_r64 = (size_t)nF * 72;
-  const size_t total = al(b_count) + al(b_sc) + 2 * al(b_cl) + al(b_bb) + al(b_tri) + al(b_rec) + al(b_r64) + 256;
+  const size_t total = al(b_count) + 2 * al(b_sc) + 2 * al(b_cl) + al(b_bb) + al(b_sup) + al(b_tri) + al(b_rec) + al(b_r64) + 256;
   unsigned char* scratch = nullptr;
   MO_CUDA(cudaMallocAsync(&scratch, total, s));
   unsigned char* p = scratch;
   int* cell_count = (int*)p; p += al(b_count);
   int* cell_fill = cell_count + ncell;
   int* coarse_cnt = cell_fill + ncell;
+  int* coarse_ncl = coarse_cnt + ncoarse;
   int2* cl_sc = (int2*)p; p += al(b_sc);
+  int2* pk_sc = (int2*)p; p += al(b_sc);
   float4* cl_c = (float4*)p; p += al(b_cl);
   float4* cl_n = (float4*)p; p += al(b_cl);
   unsigned* coarse_bb = (unsigned*)p; p += al(b_bb);
+  unsigned* super_bb = (unsigned*)p; int* super_cnt = (int*)(super_bb + 6 * nsuper); p += al(b_sup);
   int* tri_cell = (int*)p; int* tri_id = tri_cell + nF; p += al(b_tri);
   float4* rec = (float4*)p; p += al(b_rec);
   double* rec64 = (double*)p; p += al(b_r64);
@@ -765,7 +819,7 @@ int run_build(Template& T, cudaStream_t s) {
 
   MO_CUDA(cudaMemsetAsync(cell_count, 0, b_count, s));
   MO_CUDA(cudaMemsetAsync(max_ext, 0, 2 * sizeof(unsigned), s));
-  MO_CUDA(cudaMemsetAsync(T.d_stats, 0, 8 * sizeof(unsigned long long), s));
+  MO_CUDA(cudaMemsetAsync(T.d_stats, 0, 8 * kStatSlots * sizeof(unsigned long long), s));
   k_init_coarse<<<div_up((long long)ncoarse, 256), 256, 0, s>>>(coarse_bb, (int)ncoarse);
   MO_LAUNCH_CHECK();
   k_tri_count<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, nV, N, nc, ncc, cell_count, coarse_cnt, coarse_bb, tri_cell,
@@ -775,7 +829,9 @@ int run_build(Template& T, cudaStream_t s) {
   MO_LAUNCH_CHECK();
   k_tri_fill<<<div_up(nF, 256), 256, 0, s>>>(T.d_Vn, T.d_F, nF, tri_cell, cl_sc, cell_fill, rec, rec64, tri_id);
   MO_LAUNCH_CHECK();
-  k_cluster<<<div_up((long long)ncell * 32, 256), 256, 0, s>>>(cl_sc, (int)ncell, rec64, cl_c, cl_n);
+  k_cluster<<<div_up((long long)ncell * 32, 256), 256, 0, s>>>(cl_sc, (int)ncell, rec64, cl_c, cl_n, pk_sc, coarse_ncl);
+  MO_LAUNCH_CHECK();
+  k_super<<<div_up((long long)nsuper * 32, 128), 128, 0, s>>>(coarse_ncl, coarse_bb, ncc, nsc, super_cnt, super_bb);
   MO_LAUNCH_CHECK();
 
   if (T.z0 > 0 || T.z1 < N || T.tz_stride > 1) {
@@ -784,15 +840,15 @@ int run_build(Template& T, cudaStream_t s) {
   }
 
   SdfArgs A;
-  A.N = N; A.nc = nc; A.ncc = ncc; A.ntile = ntile; A.z0 = T.z0; A.z1 = T.z1;
+  A.N = N; A.nc = nc; A.ncc = ncc; A.nsc = nsc; A.ntile = ntile; A.z0 = T.z0; A.z1 = T.z1;
   // slab: the tile layers that hold slices [z0, z1); cyclic: layers tz_first, tz_first + tz_stride, ...
   A.tz0 = T.tz_stride > 1 ? T.tz_first : T.z0 / kTileZ;
   A.tz_stride = std::max(T.tz_stride, 1);
   const int n_layers = T.tz_stride > 1 ? (T.tz_first < div_up(N, kTileZ) ? div_up(div_up(N, kTileZ) - T.tz_first, T.tz_stride) : 0)
                                        : (T.z1 - 1) / kTileZ - A.tz0 + 1;
   A.ccs = (float)((double)(kCellVox * kCoarse) / N);
-  A.max_ext = max_ext; A.coarse_cnt = coarse_cnt; A.coarse_bb = coarse_bb;
-  A.cl_sc = cl_sc; A.cl_c = cl_c; A.cl_n = cl_n;
+  A.max_ext = max_ext; A.coarse_ncl = coarse_ncl; A.coarse_bb = coarse_bb;
+  A.pk_sc = pk_sc; A.cl_c = cl_c; A.cl_n = cl_n; A.super_cnt = super_cnt; A.super_bb = super_bb;
   A.rec = rec; A.rec64 = rec64; A.tri_id = tri_id;
   A.grid64 = T.d_grid64; A.grid32 = T.d_grid32; A.nearest = T.d_nearest; A.stats = T.d_stats;
   static bool attr_set[64] = {};
