@@ -112,7 +112,14 @@ int mo_template_copy_grid(int param_id, int direction, int z0, int z1, double* d
 /* Device pointer of the normalised FP64 target vertices [nV,3] (Mesh::GetV after Normalize). */
 int mo_template_vertices(int param_id, const double** d_Vn);
 
-/* Build statistics of the last grid build of this template (for roofline accounting):
+/* Distance-field builds started after mo_build_stats_enable(1) run the instrumented instantiation of the search
+ * kernel, which counts its tests for mo_template_build_stats; the default (0) runs the same search without the
+ * counters (they cost registers in the hot loops).  The counts are deterministic: an instrumented build of the same
+ * input reports what the plain build executed.  Returns the previous setting.  Process-wide. */
+int mo_build_stats_enable(int on);
+
+/* Build statistics of the last grid build of this template (for roofline accounting; all zero unless the build ran
+ * with mo_build_stats_enable(1)):
  * point-triangle tests executed in FP32 (74 FLOP each), exact FP64 re-evaluations, bounding-
  * cylinder tests of triangle clusters against a tile, a block or a voxel, and bounding-disc pre-tests of
  * single triangles against a voxel (both the same ~38 FLOP test, sdf_build.cu cyl_skip).

@@ -10,6 +10,7 @@
 namespace mo {
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_build_stats{0};
 static thread_local std::string t_error;
 void set_error(const std::string& s) { t_error = s; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
@@ -156,6 +157,7 @@ extern "C" {
 int mo_version(void) { return 1; }
 unsigned long long mo_launch_count(void) { return g_launches.load(); }
 const char* mo_last_error(void) { return t_error.c_str(); }
+int mo_build_stats_enable(int on) { return g_build_stats.exchange(on ? 1 : 0); }
 int mo_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -81,6 +81,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // every kernel launch of this library is followed by MO_LAUNCH_CHECK, which also counts it
 // (mo_launch_count: the "gpu_launches" figure of bench.py)
 extern std::atomic<unsigned long long> g_launches;
+extern std::atomic<int> g_build_stats;   // mo_build_stats_enable: distance-field builds count their tests
 #define MO_LAUNCH_CHECK()                                             \
   do {                                                                \
     ::mo::g_launches.fetch_add(1, std::memory_order_relaxed);         \

@@ -518,7 +518,22 @@ struct LaneState {
   int best_id;     // its original triangle index (lowest on exact ties)
   float ub;        // rigorous FP32 upper bound of the exact minimum
   int cnt;         // queued FP64 candidates
-  unsigned n64;
+};
+
+// test counters of the instrumented instantiation (mo_build_stats_enable); empty otherwise
+template <bool STATS> struct Counters;
+template <> struct Counters<true> {
+  unsigned n32 = 0, n64 = 0, n_cyl = 0, n_disc = 0;
+  __device__ __forceinline__ void cyl(unsigned n) { n_cyl += n; }
+  __device__ __forceinline__ void disc(unsigned n) { n_disc += n; }
+  __device__ __forceinline__ void t32(unsigned n) { n32 += n; }
+  __device__ __forceinline__ void t64(unsigned n) { n64 += n; }
+};
+template <> struct Counters<false> {
+  __device__ __forceinline__ void cyl(unsigned) {}
+  __device__ __forceinline__ void disc(unsigned) {}
+  __device__ __forceinline__ void t32(unsigned) {}
+  __device__ __forceinline__ void t64(unsigned) {}
 };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -531,29 +546,44 @@ __device__ __forceinline__ float warp_max(float v) {
 // shared memory and never synchronises with the other warps of its CTA.
 struct WarpCtx {
   float4* s_tri;      // [kRecParts][32] staged triangle records
+  float4* s_wc;       // [32] clusters of the current batch: centre, rho
+  float4* s_wn;       // [32] axis, tau
+  int2* s_wsc;        // [32] first record, count
   int* s_lid;         // [kQueueCap][32] queued FP64 candidates: record index
   float* s_lq;        // [kQueueCap][32] their FP32 lower bounds
   int lane;
   bool valid;
   float px, py, pz;
-  int vx, vy, vz, N;  // the query point is (vx/N, vy/N, vz/N) in FP64 (mesh.cc:115-117), formed when needed
 };
+
+// this lane's voxel: the CTA covers an 8x8x4 tile, the warp a 4x4x2 block of it (recomputed where needed: cheaper
+// than three live registers in the search loops)
+__device__ __forceinline__ void voxel_of_lane(const SdfArgs& A, int& bx, int& by, int& bz, int& vx, int& vy, int& vz) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile,
+            tz = A.tz0 + (blockIdx.x / (A.ntile * A.ntile)) * A.tz_stride;   // tz in units of kTileZ
+  bx = tx * kTile + (warp & 1) * 4; by = ty * kTile + ((warp >> 1) & 1) * 4; bz = tz * kTileZ + (warp >> 2) * 2;
+  vx = bx + (lane & 3); vy = by + ((lane >> 2) & 3); vz = bz + (lane >> 4);
+}
 
 // Exact FP64 evaluation of everything queued, CONVERGED over the warp: in round k every lane that still holds a k-th
 // candidate which can win evaluates it, so the (slow, branchy) FP64 routine runs with as many lanes as have work
 // instead of one lane at a time.  An entry is skipped when its FP32 lower bound exceeds the lane's upper bound: its
 // exact distance is then strictly larger than the running minimum, so it can neither win nor tie.
-__device__ __forceinline__ void warp_flush(const SdfArgs& A, const WarpCtx& w, LaneState& st) {
+template <bool STATS>
+__device__ __forceinline__ void warp_flush(const SdfArgs& A, const WarpCtx& w, LaneState& st, Counters<STATS>& cn) {
   const int maxc = __reduce_max_sync(0xffffffffu, st.cnt);
   if (maxc == 0) return;
-  const double pxd = __ddiv_rn((double)w.vx, (double)w.N), pyd = __ddiv_rn((double)w.vy, (double)w.N),
-               pzd = __ddiv_rn((double)w.vz, (double)w.N);
+  int bx, by, bz, vx, vy, vz;
+  voxel_of_lane(A, bx, by, bz, vx, vy, vz);
+  const double pxd = __ddiv_rn((double)vx, (double)A.N), pyd = __ddiv_rn((double)vy, (double)A.N),
+               pzd = __ddiv_rn((double)vz, (double)A.N);   // mesh.cc:115-117
   for (int k = 0; k < maxc; ++k) {
     if (k < st.cnt && w.s_lq[k * 32 + w.lane] <= st.ub) {
       const int gi = w.s_lid[k * 32 + w.lane];
       const double d = tri_exact64(A.rec64 + 9 * (size_t)gi, pxd, pyd, pzd);
       const int id = A.tri_id[gi];
-      st.n64++;
+      cn.t64(1u);
       if (d < st.best64 || (d == st.best64 && id < st.best_id)) {
         st.best64 = d; st.best_id = id;
         st.ub = fminf(st.ub, __double2float_ru(d));
@@ -565,7 +595,8 @@ __device__ __forceinline__ void warp_flush(const SdfArgs& A, const WarpCtx& w, L
 
 // Some lane's queue is full: first drop the entries that can no longer win (the upper bound has usually moved
 // below them since they were queued); only if a lane is still full, evaluate exactly.  Called by all 32 lanes.
-__device__ __forceinline__ void queue_make_room(const SdfArgs& A, const WarpCtx& w, LaneState& st) {
+template <bool STATS>
+__device__ __forceinline__ void queue_make_room(const SdfArgs& A, const WarpCtx& w, LaneState& st, Counters<STATS>& cn) {
   int n = 0;
   for (int k = 0; k < st.cnt; ++k) {
     const float lq = w.s_lq[k * 32 + w.lane];
@@ -575,17 +606,17 @@ __device__ __forceinline__ void queue_make_room(const SdfArgs& A, const WarpCtx&
     }
   }
   st.cnt = n;
-  if (__any_sync(0xffffffffu, st.cnt == kQueueCap)) warp_flush(A, w, st);
+  if (__any_sync(0xffffffffu, st.cnt == kQueueCap)) warp_flush(A, w, st, cn);
 }
 
 // One cluster against the warp's 32 voxels: per-voxel cylinder test, then the cluster's triangles are staged
 // 32 at a time in the warp's shared memory, pre-tested per voxel with their disc bound and evaluated in FP32
 // only if some lane still needs them.
+template <bool STATS>
 __device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx& w, LaneState& st, const float4 C,
-                                                const float4 Nm, const int2 sc, unsigned& n_cyl, unsigned& n_disc,
-                                                unsigned& n32) {
+                                                const float4 Nm, const int2 sc, Counters<STATS>& cn) {
   const bool act = w.valid && !cyl_skip(w.px, w.py, w.pz, st.ub, C, Nm);
-  n_cyl += w.valid ? 1u : 0u;
+  cn.cyl(w.valid ? 1u : 0u);
   if (!__any_sync(0xffffffffu, act)) return;
   for (int tb = 0; tb < sc.y; tb += 32) {
     const int nt = min(32, sc.y - tb);
@@ -596,16 +627,16 @@ __device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx&
       for (int part = 0; part < kRecParts; ++part) w.s_tri[part * 32 + w.lane] = __ldg(r + part);
     }
     __syncwarp();
-    n_disc += w.valid ? (unsigned)nt : 0u;
+    cn.disc(w.valid ? (unsigned)nt : 0u);
     for (int j = 0; j < nt; ++j) {
       const bool need = act && !cyl_skip(w.px, w.py, w.pz, st.ub, w.s_tri[4 * 32 + j], w.s_tri[5 * 32 + j]);
       if (!__any_sync(0xffffffffu, need)) continue;
-      n32 += w.valid ? 1u : 0u;
+      cn.t32(w.valid ? 1u : 0u);
       float e;
       const float q = tri_q(w.s_tri[j], w.s_tri[32 + j], w.s_tri[64 + j], w.s_tri[96 + j], w.px, w.py, w.pz, e);
       const float qlo = q - e;
       const bool push = w.valid && qlo <= st.ub;
-      if (__any_sync(0xffffffffu, push && st.cnt == kQueueCap)) queue_make_room(A, w, st);
+      if (__any_sync(0xffffffffu, push && st.cnt == kQueueCap)) queue_make_room(A, w, st, cn);
       if (push && qlo <= st.ub) {
         w.s_lid[st.cnt * 32 + w.lane] = sc.x + tb + j;
         w.s_lq[st.cnt * 32 + w.lane] = qlo;
@@ -617,12 +648,12 @@ __device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx&
 }
 
 // gap^2 between an AABB stored as ordered uints (lo xyz, hi xyz) and the block's sample box
-__device__ __forceinline__ float aabb_gap2(const unsigned* __restrict__ bb, const float blo[3], const float bhi[3]) {
+__device__ __forceinline__ float aabb_gap2(const unsigned* __restrict__ bb, const float* s_box) {
   float d2 = 0.f;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const float lo = o2f(__ldg(bb + j)), hi = o2f(__ldg(bb + 3 + j));
-    const float gap = fmaxf(0.f, fmaxf(lo - bhi[j], blo[j] - hi));
+    const float gap = fmaxf(0.f, fmaxf(lo - s_box[3 + j], s_box[j] - hi));
     d2 = fmaf(gap, gap, d2);
   }
   return d2;
@@ -643,7 +674,7 @@ __device__ __forceinline__ int take_nearest(float& k0, float& k1, const float bo
   return src + 32 * which;
 }
 
-constexpr int kWarpSmem = kRecParts * 32 * 16 + kQueueCap * 32 * 8;   // bytes of shared memory per warp
+constexpr int kWarpSmem = (kRecParts * 32 + 32 + 32) * 16 + 32 * 8 + kQueueCap * 32 * 8 + 32;   // bytes of shared memory per warp
 constexpr size_t kSdfSmem = (size_t)kWarps * kWarpSmem;
 
 // One warp per 4x4x2-voxel block, one lane per voxel; the eight warps of a CTA cover an 8x8x4 tile (neighbouring
@@ -652,41 +683,49 @@ constexpr size_t kSdfSmem = (size_t)kWarps * kWarpSmem;
 // box with the block's largest running bound; the sweep stops when the ring's lower bound exceeds it), tests the
 // clusters of every surviving coarse cell against the block (lanes over clusters, ballot + compaction) and hands the
 // survivors to process_cluster (lanes over voxels).
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = A.N, ncc = A.ncc;
-  const int tx = blockIdx.x % A.ntile, ty = (blockIdx.x / A.ntile) % A.ntile, tz = A.tz0 + (blockIdx.x / (A.ntile * A.ntile)) * A.tz_stride;   // tz in units of kTileZ
-
   WarpCtx w;
+  float* s_box;   // [6] the block's sample box (lo xyz, hi xyz), read by the coarse levels only
   {
     unsigned char* base = smem_raw + (size_t)warp * kWarpSmem;
     w.s_tri = reinterpret_cast<float4*>(base);
-    w.s_lid = reinterpret_cast<int*>(w.s_tri + kRecParts * 32);
+    w.s_wc = w.s_tri + kRecParts * 32;
+    w.s_wn = w.s_wc + 32;
+    w.s_wsc = reinterpret_cast<int2*>(w.s_wn + 32);
+    w.s_lid = reinterpret_cast<int*>(w.s_wsc + 32);
     w.s_lq = reinterpret_cast<float*>(w.s_lid + kQueueCap * 32);
+    s_box = w.s_lq + kQueueCap * 32;
   }
-  // this lane's voxel; the warp owns a 4x4x2 block of the tile
-  const int bx = tx * kTile + (warp & 1) * 4, by = ty * kTile + ((warp >> 1) & 1) * 4, bz = tz * kTileZ + (warp >> 2) * 2;
-  const int vx = bx + (lane & 3), vy = by + ((lane >> 2) & 3), vz = bz + (lane >> 4);
+  int bx, by, bz, vx, vy, vz;
+  voxel_of_lane(A, bx, by, bz, vx, vy, vz);
   const double invN = 1.0 / (double)N;
   w.lane = lane;
   w.valid = vx < N && vy < N && vz < N && vz >= A.z0 && vz < A.z1;
   if (!__any_sync(0xffffffffu, w.valid)) return;   // the whole block lies outside the grid or the slab
-  w.vx = vx; w.vy = vy; w.vz = vz; w.N = N;
   w.px = (float)__ddiv_rn((double)vx, (double)N); w.py = (float)__ddiv_rn((double)vy, (double)N);
   w.pz = (float)__ddiv_rn((double)vz, (double)N);   // mesh.cc:115-117, rounded once to FP32 for the search
+  // (opaque to the compiler: under register pressure it would otherwise re-run the FP64 division and the quarter-rate
+  //  conversion inside the search loops instead of keeping three registers)
+  asm volatile("" : "+f"(w.px), "+f"(w.py), "+f"(w.pz));
   const bool valid = w.valid;
   // block bounding sphere (sample points, unclipped) and sample box (clipped to the grid and the slab)
   const float wcx = (float)((bx + 1.5) * invN), wcy = (float)((by + 1.5) * invN), wcz = (float)((bz + 0.5) * invN);
   const float Rw = (float)(2.1795 * invN * 1.0001);   // half diagonal of the 3x3x1-interval sample box
-  const float blo[3] = {(float)(bx * invN), (float)(by * invN), (float)(max(bz, A.z0) * invN)};
-  const float bhi[3] = {(float)(min(bx + 3, N - 1) * invN), (float)(min(by + 3, N - 1) * invN),
-                        (float)(min(min(bz + 1, N - 1), A.z1 - 1) * invN)};
+  if (lane == 0) {
+    s_box[0] = (float)(bx * invN); s_box[1] = (float)(by * invN); s_box[2] = (float)(max(bz, A.z0) * invN);
+    s_box[3] = (float)(min(bx + 3, N - 1) * invN); s_box[4] = (float)(min(by + 3, N - 1) * invN);
+    s_box[5] = (float)(min(min(bz + 1, N - 1), A.z1 - 1) * invN);
+  }
+  __syncwarp();
 
   const float kInf = __int_as_float(0x7f800000);
   LaneState st;
-  st.best64 = DBL_MAX; st.best_id = -1; st.ub = kInf; st.cnt = 0; st.n64 = 0;
-  unsigned n32 = 0, n_cyl = 0, n_disc = 0;
+  st.best64 = DBL_MAX; st.best_id = -1; st.ub = kInf; st.cnt = 0;
+  Counters<STATS> cn;
   float ubw = kInf;       // max ub over the block's voxels
   float thr_w = kInf;     // (sqrt(ubw) + Rw)^2
 
@@ -700,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
     for (int h = 0; h < 2; ++h) {
       const int S = sb + 32 * h + lane;
       sk[h] = kInf;
-      if (S < nsup && __ldg(&A.super_cnt[S]) > 0) sk[h] = aabb_gap2(A.super_bb + 6 * (size_t)S, blo, bhi);
+      if (S < nsup && __ldg(&A.super_cnt[S]) > 0) sk[h] = aabb_gap2(A.super_bb + 6 * (size_t)S, s_box);
     }
     for (;;) {
       const int ss = take_nearest(sk[0], sk[1], ubw, lane);
@@ -708,20 +747,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
       const int S = sb + ss;
       const int sx = S % nsc, sy = (S / nsc) % nsc, sz = S / (nsc * nsc);
       float ck[2];
-      int cidx[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int l = 32 * h + lane;
         const int cx = 4 * sx + (l & 3), cy = 4 * sy + ((l >> 2) & 3), cz = 4 * sz + (l >> 4);
+        const int ci = (cz * ncc + cy) * ncc + cx;
         ck[h] = kInf;
-        cidx[h] = (cz * ncc + cy) * ncc + cx;
-        if (cx < ncc && cy < ncc && cz < ncc && __ldg(&A.coarse_ncl[cidx[h]]) > 0)
-          ck[h] = aabb_gap2(A.coarse_bb + 6 * (size_t)cidx[h], blo, bhi);
+        if (cx < ncc && cy < ncc && cz < ncc && __ldg(&A.coarse_ncl[ci]) > 0) ck[h] = aabb_gap2(A.coarse_bb + 6 * (size_t)ci, s_box);
       }
       for (;;) {
         const int cs = take_nearest(ck[0], ck[1], ubw, lane);
         if (cs < 0) break;
-        const int cc = __shfl_sync(0xffffffffu, cs >= 32 ? cidx[1] : cidx[0], cs & 31);
+        const int cc = ((4 * sz + (cs >> 4)) * ncc + 4 * sy + ((cs >> 2) & 3)) * ncc + 4 * sx + (cs & 3);
         const int ncl = __ldg(&A.coarse_ncl[cc]);
         // ---- the clusters of this coarse cell against the block: lanes over clusters, nearest first, every
         //      survivor re-checked against the block's bound when it has tightened -----------------------------
@@ -729,23 +766,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
           const int j = b + lane;
           const bool has = j < ncl;
           const int cell = cc * 64 + (has ? j : 0);
-          const float4 C = __ldg(&A.cl_c[cell]), Nm = __ldg(&A.cl_n[cell]);
-          const int2 sc = __ldg(&A.pk_sc[cell]);
-          unsigned key = has ? __float_as_uint(cyl_lb2(wcx, wcy, wcz, C, Nm)) : 0x7f800000u;   // ordering only (>= 0: bits are monotone)
-          n_cyl += has ? 2u : 0u;
+          unsigned key = 0x7f800000u;
+          __syncwarp();
+          if (has) {
+            // the batch lives in the warp's shared memory (registers are needed by the inner loops); every lane keeps
+            // only the ordering key of its cluster
+            const float4 C = __ldg(&A.cl_c[cell]), Nm = __ldg(&A.cl_n[cell]);
+            w.s_wc[lane] = C; w.s_wn[lane] = Nm; w.s_wsc[lane] = __ldg(&A.pk_sc[cell]);
+            key = __float_as_uint(cyl_lb2(wcx, wcy, wcz, C, Nm));   // ordering only (>= 0: the bit patterns are monotone)
+          }
+          __syncwarp();
+          cn.cyl(has ? 2u : 0u);
           bool recheck = true;
           for (;;) {
-            if (recheck && key != 0x7f800000u && cyl_skip(wcx, wcy, wcz, thr_w, C, Nm)) key = 0x7f800000u;
+            if (recheck && key != 0x7f800000u && cyl_skip(wcx, wcy, wcz, thr_w, w.s_wc[lane], w.s_wn[lane])) key = 0x7f800000u;
             const unsigned bk = __reduce_min_sync(0xffffffffu, key);
             if (bk == 0x7f800000u) break;
             const int who = __ffs(__ballot_sync(0xffffffffu, key == bk)) - 1;
-            const float4 fC = make_float4(__shfl_sync(0xffffffffu, C.x, who), __shfl_sync(0xffffffffu, C.y, who),
-                                          __shfl_sync(0xffffffffu, C.z, who), __shfl_sync(0xffffffffu, C.w, who));
-            const float4 fN = make_float4(__shfl_sync(0xffffffffu, Nm.x, who), __shfl_sync(0xffffffffu, Nm.y, who),
-                                          __shfl_sync(0xffffffffu, Nm.z, who), __shfl_sync(0xffffffffu, Nm.w, who));
-            const int2 fsc = make_int2(__shfl_sync(0xffffffffu, sc.x, who), __shfl_sync(0xffffffffu, sc.y, who));
+            const float4 fC = w.s_wc[who], fN = w.s_wn[who];
+            const int2 fsc = w.s_wsc[who];
             if (lane == who) key = 0x7f800000u;
-            process_cluster(A, w, st, fC, fN, fsc, n_cyl, n_disc, n32);
+            process_cluster(A, w, st, fC, fN, fsc, cn);
             const float nub = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(st.ub) : 0u));
             recheck = nub < ubw;
             if (recheck) {
@@ -760,24 +801,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
   }
 
   // ---- exact FP64 evaluation of everything still queued, then store ------------------
-  warp_flush(A, w, st);
+  warp_flush(A, w, st, cn);
   if (valid) {
+    voxel_of_lane(A, bx, by, bz, vx, vy, vz);
     const size_t o = ((size_t)vz * N + vy) * N + vx;
     const double d = st.best_id >= 0 ? __dsqrt_rn(st.best64) : 1e30;   // mesh.cc:146
     A.grid64[o] = d;
     A.grid32[o] = (float)d;
     A.nearest[o] = st.best_id;
   }
-  unsigned long long a32 = n32, a64 = st.n64, ac = n_cyl, as = n_disc;
-  for (int o = 16; o > 0; o >>= 1) {
-    a32 += __shfl_xor_sync(0xffffffffu, a32, o);
-    a64 += __shfl_xor_sync(0xffffffffu, a64, o);
-    ac += __shfl_xor_sync(0xffffffffu, ac, o);
-    as += __shfl_xor_sync(0xffffffffu, as, o);
-  }
-  if (lane == 0) {
-    unsigned long long* slot = A.stats + 8 * ((blockIdx.x * kWarps + warp) % kStatSlots);
-    atomicAdd(slot + 0, a32); atomicAdd(slot + 1, a64); atomicAdd(slot + 2, ac); atomicAdd(slot + 4, as);
+  if constexpr (STATS) {
+    unsigned long long a32 = cn.n32, a64 = cn.n64, ac = cn.n_cyl, as = cn.n_disc;
+    for (int o = 16; o > 0; o >>= 1) {
+      a32 += __shfl_xor_sync(0xffffffffu, a32, o);
+      a64 += __shfl_xor_sync(0xffffffffu, a64, o);
+      ac += __shfl_xor_sync(0xffffffffu, ac, o);
+      as += __shfl_xor_sync(0xffffffffu, as, o);
+    }
+    if (lane == 0) {
+      unsigned long long* slot = A.stats + 8 * ((blockIdx.x * kWarps + warp) % kStatSlots);
+      atomicAdd(slot + 0, a32); atomicAdd(slot + 1, a64); atomicAdd(slot + 2, ac); atomicAdd(slot + 4, as);
+    }
   }
 }
 
@@ -853,12 +897,16 @@ int run_build(Template& T, cudaStream_t s) {
   A.grid64 = T.d_grid64; A.grid32 = T.d_grid32; A.nearest = T.d_nearest; A.stats = T.d_stats;
   static bool attr_set[64] = {};
   if (!attr_set[T.device & 63]) {
-    MO_CUDA(cudaFuncSetAttribute(k_sdf_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem));
+    MO_CUDA(cudaFuncSetAttribute(k_sdf_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem));
+    MO_CUDA(cudaFuncSetAttribute(k_sdf_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem));
     attr_set[T.device & 63] = true;
   }
   const int ntiles = ntile * ntile * n_layers;
   if (ntiles > 0) {
-    k_sdf_tiles<<<ntiles, kThreads, kSdfSmem, s>>>(A);
+    // the instrumented instantiation counts its tests for mo_template_build_stats (mo_build_stats_enable); the plain
+    // one runs the same search without the counters
+    if (g_build_stats.load(std::memory_order_relaxed)) k_sdf_tiles<true><<<ntiles, kThreads, kSdfSmem, s>>>(A);
+    else k_sdf_tiles<false><<<ntiles, kThreads, kSdfSmem, s>>>(A);
     MO_LAUNCH_CHECK();
   }
   MO_CUDA(cudaFreeAsync(scratch, s));

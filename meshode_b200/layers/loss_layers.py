@@ -13,7 +13,10 @@ Differences from the reference, all additive or bug-for-bug documented:
     normalised IN PLACE as in the reference when it already lives there;
   * CadLossFunction.forward passes ``param_id`` (the reference omits it, cad_loss_layer.py:10-11,
     and would raise TypeError);
-  * the scalar loss is accumulated in float64 and returned as float32.
+  * the scalar loss is accumulated in float64 and returned as float32;
+  * forward/backward use the edge connectivity captured by Store*Information: the ``src_F`` / ``src_E`` handed to
+    ``forward`` (or to the ``*LossFunction.apply``) are accepted for the reference's signature and not re-read
+    (the reference iterates the caller's tensors against the stored rest vectors: rigid_layer.cc:113-130).
 """
 import torch
 from torch import nn
@@ -46,6 +49,19 @@ class _FusedLoss(Function):
         return grad_h * grad, None, None, None, None
 
 
+def _function_forward(ctx, V, dist_pid, edge_pid, w_edge, mask_threshold):
+    """forward of the exported autograd Functions: one fused launch gives the loss and its gradient, the gradient is
+    kept for backward (the reference recomputes it there: rigid_loss_layer.py:20-27)."""
+    loss, grad = pyDeform.LossForwardBackward(V.detach().contiguous(), dist_pid, edge_pid, w_edge, mask_threshold, True, True)
+    ctx.save_for_backward(grad)
+    return loss.to(torch.float32)
+
+
+def _function_backward(ctx, grad_h, n_inputs):
+    (grad,) = ctx.saved_tensors
+    return (grad_h * grad,) + (None,) * (n_inputs - 1)
+
+
 def _to_device(t, device):
     return t if t.device == device else t.to(device)
 
@@ -67,10 +83,17 @@ class _TemplateLayer(nn.Module):
 
 # ---- rigid_loss_layer.py --------------------------------------------------------------------------
 class RigidLossFunction(Function):
+    """rigid_loss_layer.py:7-27: ``RigidLossFunction.apply(src_V, src_F, param_id)``, differentiable in src_V.  The edge
+    connectivity is the one captured by StoreRigidityInformation (``src_F`` is accepted for the signature)."""
+
     @staticmethod
     def forward(ctx, src_V, src_F, param_id):
         pid = _pid(param_id)
-        return _FusedLoss.apply(src_V, pid, pid, 1.0, 0.0)
+        return _function_forward(ctx, src_V, pid, pid, 1.0, 0.0)
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        return _function_backward(ctx, grad_h, 3)
 
 
 class RigidLossLayer(_TemplateLayer):
@@ -95,10 +118,16 @@ def Finalize(src_V, param_id):
 
 # ---- graph_loss_layer.py --------------------------------------------------------------------------
 class GraphLossFunction(Function):
+    """graph_loss_layer.py:9-43 (distance gradient masked to vertices with 0.5*d^2 < 0.5*0.03^2)."""
+
     @staticmethod
     def forward(ctx, src_V, src_E, rigidity2, param_id):
         pid = _pid(param_id)
-        return _FusedLoss.apply(src_V, pid, pid, float(rigidity2), GRAPH_MASK)
+        return _function_forward(ctx, src_V, pid, pid, float(rigidity2), GRAPH_MASK)
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        return _function_backward(ctx, grad_h, 4)
 
 
 class GraphLossLayer(_TemplateLayer):
@@ -119,10 +148,16 @@ class GraphLossLayer(_TemplateLayer):
 
 # ---- graph_loss2_layer.py -------------------------------------------------------------------------
 class GraphLoss2Function(Function):
+    """graph_loss2_layer.py:9-41."""
+
     @staticmethod
     def forward(ctx, V1, E1, rigidity2, param_id1, param_id2):
         # distance to the OTHER mesh (param_id2), edges of its own (param_id1): graph_loss2_layer.py:18-19
-        return _FusedLoss.apply(V1, _pid(param_id2), _pid(param_id1), float(rigidity2), 0.0)
+        return _function_forward(ctx, V1, _pid(param_id2), _pid(param_id1), float(rigidity2), 0.0)
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        return _function_backward(ctx, grad_h, 5)
 
 
 class GraphLoss2Layer(_TemplateLayer):
@@ -147,10 +182,16 @@ class GraphLoss2Layer(_TemplateLayer):
 
 # ---- cad_loss_layer.py ----------------------------------------------------------------------------
 class CadLossFunction(Function):
+    """cad_loss_layer.py:7-27 (with the param_id the reference forgets to pass to its forward calls, :10-11)."""
+
     @staticmethod
     def forward(ctx, src_V, src_F, src_E, param_id):
         pid = _pid(param_id)
-        return _FusedLoss.apply(src_V, pid, pid, 1.0, 0.0)
+        return _function_forward(ctx, src_V, pid, pid, 1.0, 0.0)
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        return _function_backward(ctx, grad_h, 4)
 
 
 class CadLossLayer(_TemplateLayer):

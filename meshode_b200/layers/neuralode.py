@@ -68,3 +68,39 @@ class NeuralODE:
 
     def integrate(self, u, t1, t2, device):
         return odeint_rk4(self.func, u, torch.tensor([t1, t2], dtype=torch.float32, device=device))[1]
+
+
+# Checkpoints: the reference pickles the objects themselves -- torch.save({'func': func, 'optim': optimizer})
+# (src/python/cad_neural_deform2.py:108) -- and its consumer reads checkpoint['func'] / ['optim'] back as objects
+# (src/python/cad_neural_animate.py:52-57).  Pickle records the defining module, so the classes carry the reference's
+# module path (served by the top-level ``layers/neuralode_fast.py``): a checkpoint written here loads in the reference's
+# tooling and the other way round.
+ODEFunc.__module__ = "layers.neuralode_fast"
+NeuralODE.__module__ = "layers.neuralode_fast"
+
+
+def save_checkpoint(path, func, optimizer):
+    """The reference's layout: {'func': NeuralODE object, 'optim': optimizer object}."""
+    import layers.neuralode_fast  # noqa: F401  (the pickled module path must resolve to these classes)
+    torch.save({"func": func, "optim": optimizer}, path)
+
+
+def load_checkpoint(path, device, lr=1e-3):
+    """Returns (func, optimizer) from a checkpoint in the reference's layout (pickled objects) or in the
+    state_dict layout written by round 1 of this repository ({'func': ODEFunc.state_dict(), 'optim':
+    Adam.state_dict()})."""
+    import layers.neuralode_fast  # noqa: F401
+    ck = torch.load(path, map_location=device, weights_only=False)
+    f, o = ck["func"], ck["optim"]
+    if isinstance(f, dict):
+        func = NeuralODE(device)
+        func.func.load_state_dict(f)
+    else:
+        func = f
+        func.to_device(device)
+    if isinstance(o, dict):
+        optimizer = torch.optim.Adam(func.parameters(), lr=lr)
+        optimizer.load_state_dict(o)
+    else:
+        optimizer = o
+    return func, optimizer

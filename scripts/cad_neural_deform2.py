@@ -15,7 +15,7 @@ import torch.optim as optim  # noqa: E402
 
 import pyDeform  # noqa: E402
 from meshode_b200.layers.graph_loss2_layer import GraphLoss2Layer  # noqa: E402
-from meshode_b200.layers.neuralode import NeuralODE  # noqa: E402
+from meshode_b200.layers.neuralode import NeuralODE, load_checkpoint, save_checkpoint  # noqa: E402
 from meshode_b200.layers.reverse_loss_layer import ReverseLossLayer  # noqa: E402
 
 parser = argparse.ArgumentParser(description='Rigid Deformation.')
@@ -26,6 +26,7 @@ parser.add_argument('--rigidity', default='0.1')
 parser.add_argument('--device', default='cuda')
 parser.add_argument('--save_path', default='./cad-output.ckpt')
 parser.add_argument('--niter', type=int, default=1000)
+parser.add_argument('--resume_path', default='')
 args = parser.parse_args()
 
 rigidity = float(args.rigidity)
@@ -41,8 +42,11 @@ V2, F2, E2, V2G2, GV2, GE2 = pyDeform.LoadCadMesh(args.target)
 graph_loss = GraphLoss2Layer(V1, F1, GV1, GE1, V2, F2, GV2, GE2, rigidity, device)   # normalises GV1 / GV2 in place
 param_id1, param_id2 = graph_loss.param_id1, graph_loss.param_id2
 reverse_loss = ReverseLossLayer()
-func = NeuralODE(device)
-optimizer = optim.Adam(func.parameters(), lr=1e-3)
+if args.resume_path != '' and os.path.exists(args.resume_path):
+    func, optimizer = load_checkpoint(args.resume_path, device)   # the reference's layout or round 1's state_dicts
+else:
+    func = NeuralODE(device)
+    optimizer = optim.Adam(func.parameters(), lr=1e-3)
 GV1_device, GV2_device = GV1.to(device), GV2.to(device)
 GV1_origin, GV2_origin = GV1_device.clone(), GV2_device.clone()
 
@@ -62,7 +66,7 @@ for it in range(0, args.niter):
              np.sqrt(loss2_forward.item() / GV2.shape[0]), np.sqrt(loss2_backward.item() / GV1.shape[0])))
 
 if args.save_path != '':
-    torch.save({'func': func.func.state_dict(), 'optim': optimizer.state_dict()}, args.save_path)
+    save_checkpoint(args.save_path, func, optimizer)   # {'func': func, 'optim': optimizer}, as cad_neural_deform2.py:108
 
 V1_copy = V1.clone()
 pyDeform.NormalizeByTemplate(V1_copy, param_id1.tolist())

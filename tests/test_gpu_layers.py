@@ -227,3 +227,56 @@ def test_neuralode_flow_with_graph_loss(pd, pair):
     from meshode_b200.layers.neuralode import odeint_rk4
     y = odeint_rk4(lambda t, y: -y, torch.ones(1, dtype=torch.float64), torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64))
     assert abs(y[-1].item() - np.exp(-1.0)) < 1e-3
+
+
+def test_exported_autograd_functions_are_differentiable(oracle, pd, pair):
+    """The reference exports RigidLossFunction / GraphLossFunction / GraphLoss2Function / CadLossFunction as autograd
+    Functions with a working backward (rigid_loss_layer.py:7-27, graph_loss_layer.py:9-43, graph_loss2_layer.py:9-41,
+    cad_loss_layer.py:7-27): ``X.apply(...).backward()`` must give the gradient the layers give."""
+    from meshode_b200.layers import (CadLossFunction, GraphLoss2Function, GraphLossFunction, RigidLossFunction)
+    import pyDeform as top
+    srcV, srcF, tarV, tarF, E = pair
+    N = 32
+    pid = pd.InitializeDeformTemplate(_t(tarV), _t(tarF), 0, N)
+    pid2 = pd.InitializeDeformTemplate(_t(srcV), _t(srcF), 0, N)
+    tm = oracle.Template(tarV, tarF, N)
+    src_n = oracle.normalize_by_template(srcV, tm.scale, tm.trans)
+    mv = _moved(src_n)
+    F_, E_ = _t(srcF), _t(E)
+    pidt = torch.tensor(pid)
+
+    # rigid
+    pd.StoreRigidityInformation(_t(src_n), F_, pid)
+    p = torch.nn.Parameter(_t(mv))
+    loss = RigidLossFunction.apply(p, F_, pidt)
+    (3.0 * loss).backward()
+    rest = oracle.store_rigid(src_n, srcF)
+    g = oracle.distfield_backward(tm.grid, mv) + oracle.rigid_backward(mv, srcF, rest)
+    assert np.array_equal(p.grad.cpu().numpy(), np.float32(3.0) * g)
+
+    # graph (mask 0.5*0.03^2 on the distance gradient, rigidity^2 on the edge term)
+    pd.StoreGraphInformation(_t(src_n), E_, pid)
+    p = torch.nn.Parameter(_t(mv))
+    GraphLossFunction.apply(p, E_, torch.tensor(1.7 * 1.7), pidt).backward()
+    grest = oracle.store_graph(src_n, E)
+    d = oracle.distfield_backward(tm.grid, mv)
+    d[~(0.5 * oracle.distfield_forward(tm.grid, mv) < np.float32(0.5 * 0.03 * 0.03))] = 0
+    want = d + oracle.graph_backward(mv, E, grest) * np.float32(1.7 * 1.7)
+    _close(p.grad.cpu().numpy(), want, 1e-6)
+
+    # graph2: distance field of the OTHER template (pid2), edges stored in its own (pid)
+    p = torch.nn.Parameter(_t(mv))
+    GraphLoss2Function.apply(p, E_, torch.tensor(1.0), pidt, torch.tensor(pid2)).backward()
+    g64_2, _, _ = pd.GetGrid(pid2)
+    want = oracle.distfield_backward(g64_2.cpu().numpy(), mv) + oracle.graph_backward(mv, E, grest)
+    assert np.array_equal(p.grad.cpu().numpy(), want)
+
+    # cad
+    pd.StoreCadInformation(_t(src_n), F_, E_, pid)
+    p = torch.nn.Parameter(_t(mv))
+    CadLossFunction.apply(p, F_, E_, pidt).backward()
+    crest, lam = oracle.store_cad(src_n, srcF, E)
+    want = oracle.distfield_backward(tm.grid, mv) + oracle.cad_backward(mv, srcF, E, crest, lam)
+    assert np.array_equal(p.grad.cpu().numpy(), want)
+    assert top.DistanceFieldLoss_forward is pd.DistanceFieldLoss_forward   # the top-level shim is the same module surface
+    pd.DestroyTemplate(pid); pd.DestroyTemplate(pid2)

@@ -64,7 +64,19 @@ def test_grid_cfg1_full_resolution(meshes, oracle, pd, N):
     np.testing.assert_allclose(g64, ref, rtol=1e-5, atol=0)
     assert np.array_equal(g64, ref)
     assert np.array_equal(idx, ridx)
-    stats = __import__("meshode_b200.capi", fromlist=["x"]).template_build_stats(pid)
+    capi = __import__("meshode_b200.capi", fromlist=["x"])
+    stats = capi.template_build_stats(pid)
+    assert stats["fp32_tests"] == 0 and stats["fp64_tests"] == 0   # the plain build does not count
+    pd.DestroyTemplate(pid)
+    # the instrumented instantiation of the search kernel: the same field, plus its test counts
+    assert capi.lib().mo_build_stats_enable(1) == 0
+    try:
+        pid = pd.InitializeDeformTemplate(_t(tarV), _t(tarF), 0, N)
+    finally:
+        assert capi.lib().mo_build_stats_enable(0) == 1
+    h64, _, hidx = [t.cpu().numpy() for t in pd.GetGrid(pid)]
+    assert np.array_equal(h64, ref) and np.array_equal(hidx, ridx)
+    stats = capi.template_build_stats(pid)
     assert stats["fp32_tests"] > 0 and stats["fp64_tests"] >= N ** 3
     pd.DestroyTemplate(pid)
 

@@ -96,3 +96,54 @@ def test_scripts_expose_the_reference_command_lines():
         assert p.returncode == 0, p.stderr[-1000:]
         for f in flags:
             assert f in p.stdout, (name, f)
+
+
+def test_reference_import_paths_and_function_surface():
+    """`import pyDeform` and `from layers.X import ...` resolve with the repository root on the path, as the reference's
+    scripts import them (src/python/rigid_deform.py:10-11, cad_neural_deform2.py:9-13); the exported autograd Functions
+    define their own backward (the reference's are differentiable)."""
+    import torch  # noqa: F401  (torch first, README.md:46-50)
+    import pyDeform
+    from torch.autograd import Function
+    from layers.cad_loss_layer import CadLossFunction, CadLossLayer, Finalize as cad_finalize  # noqa: F401
+    from layers.graph_loss2_layer import Finalize as g2_finalize, GraphLoss2Function, GraphLoss2Layer  # noqa: F401
+    from layers.graph_loss_layer import Finalize as g_finalize, GraphLossFunction, GraphLossLayer  # noqa: F401
+    from layers.neuralode_fast import NeuralODE
+    from layers.reverse_loss_layer import ReverseLossLayer  # noqa: F401
+    from layers.rigid_loss_layer import Finalize, RigidLossFunction, RigidLossLayer  # noqa: F401
+    for fn in (RigidLossFunction, GraphLossFunction, GraphLoss2Function, CadLossFunction):
+        assert fn.backward is not Function.backward and fn.forward is not Function.forward
+    for name in ("LoadMesh", "LoadCadMesh", "SaveMesh", "InitializeDeformTemplate", "NormalizeByTemplate",
+                 "DenormalizeByTemplate", "SolveLinear", "DistanceFieldLoss_forward", "DistanceFieldLoss_backward",
+                 "RigidEdgeLoss_forward", "RigidEdgeLoss_backward", "StoreRigidityInformation", "CadEdgeLoss_forward",
+                 "CadEdgeLoss_backward", "StoreCadInformation", "GraphEdgeLoss_forward", "GraphEdgeLoss_backward",
+                 "StoreGraphInformation"):   # src/interface/pydeform.cc:14-39
+        assert callable(getattr(pyDeform, name))
+    assert NeuralODE.__module__ == "layers.neuralode_fast"
+
+
+def test_checkpoint_layout_is_the_references(tmp_path):
+    """cad_neural_deform2.py:108 pickles {'func': func, 'optim': optimizer}; cad_neural_animate.py:52-57 reads the
+    objects back.  The file written here has that layout under the reference's module path, and the loader also
+    accepts the state_dict layout of this repository's first round."""
+    import zipfile
+    import torch
+    from meshode_b200.layers.neuralode import NeuralODE, load_checkpoint, save_checkpoint
+    f = NeuralODE(torch.device("cpu"))
+    o = torch.optim.Adam(f.parameters(), lr=1e-3)
+    f.forward(torch.rand(10, 3)).sum().backward()
+    o.step()
+    p = str(tmp_path / "a.ckpt")
+    save_checkpoint(p, f, o)
+    z = zipfile.ZipFile(p)
+    data = z.read([n for n in z.namelist() if n.endswith("data.pkl")][0])
+    assert b"layers.neuralode_fast" in data and b"meshode_b200" not in data
+    ck = torch.load(p, map_location="cpu", weights_only=False)
+    assert isinstance(ck["func"], NeuralODE) and isinstance(ck["optim"], torch.optim.Adam)   # objects, as the reference reads them
+    x = torch.rand(7, 3)
+    f2, o2 = load_checkpoint(p, torch.device("cpu"))
+    assert torch.equal(f.forward(x), f2.forward(x)) and torch.equal(f.integrate(x, 0, 0.4, "cpu"), f2.integrate(x, 0, 0.4, "cpu"))
+    assert o2.state_dict()["state"][0]["step"] == o.state_dict()["state"][0]["step"]
+    torch.save({"func": f.func.state_dict(), "optim": o.state_dict()}, p)
+    f3, o3 = load_checkpoint(p, torch.device("cpu"))
+    assert torch.equal(f.forward(x), f3.forward(x))

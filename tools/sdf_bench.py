@@ -24,8 +24,13 @@ for k in range(reps + 2):
     torch.cuda.synchronize()
     if k >= 2:
         ts.append(e0.elapsed_time(e1))
-    st = capi.template_build_stats(pid)
     pd.DestroyTemplate(pid)
+# the counts come from one instrumented build (the timed ones run without the counters)
+capi.lib().mo_build_stats_enable(1)
+pid = pd.InitializeDeformTemplate(tV, tF, 0, N)
+st = capi.template_build_stats(pid)
+pd.DestroyTemplate(pid)
+capi.lib().mo_build_stats_enable(0)
 nvox = N ** 3
 print("N=%d tris=%d: %.3f ms (min %.3f) | per voxel: dense %.1f  disc %.1f  cluster %.1f  fp64 %.2f" %
       (N, F.shape[0], np.mean(ts), np.min(ts), st["fp32_tests"] / nvox, st["disc_tests"] / nvox, st["cull_tests"] / nvox,
