@@ -50,7 +50,7 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
-APPS = ["rigid_deform", "rigid_rot_deform"]
+APPS = ["rigid_deform", "rigid_rot_deform", "cad_deform"]
 BIN = os.path.join(HERE, "bin")
 
 

@@ -163,3 +163,55 @@ def test_cad_neural_deform2(tmp_path, meshes):
     assert len(tot) == 12 and np.isfinite(tot).all() and tot[-1] < tot[0]
     oV, oF = _read_obj(o_obj)
     assert np.isfinite(oV).all() and oF.max() < oV.shape[0] and os.path.exists(str(tmp_path / "flow.ckpt"))
+    # the checkpoint has the reference's layout ({'func': NeuralODE object, 'optim': optimizer}, cad_neural_deform2.py:108)
+    # and resumes: the first loss line of a resumed run continues from the trained flow, not from a fresh one
+    sys.path.insert(0, ROOT)
+    ck = torch.load(str(tmp_path / "flow.ckpt"), map_location="cpu", weights_only=False)
+    assert type(ck["func"]).__name__ == "NeuralODE" and isinstance(ck["optim"], torch.optim.Adam)
+    p2 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cad_neural_deform2.py"), "--source", s_obj, "--target", t_obj,
+                         "--output", o_obj, "--niter", "2", "--save_path", "", "--resume_path", str(tmp_path / "flow.ckpt")],
+                        capture_output=True, text=True, timeout=900)
+    assert p2.returncode == 0, p2.stderr[-3000:]
+    tot2 = [sum(float(x) for x in m) for m in re.findall(
+        r"loss1_forward=([0-9.eE+-]+) loss1_backward=([0-9.eE+-]+) loss2_forward=([0-9.eE+-]+) loss2_backward=([0-9.eE+-]+)", p2.stdout)]
+    assert len(tot2) == 2 and tot2[0] < tot[0] and tot2[0] <= 1.05 * tot[-1]
+
+
+def test_cad_deform_driver_cfg2_pair(tmp_path, meshes):
+    """The re-hosted cad_deform (reference src/app/cad_deform.cc:21-120) on the shipped CAD pair: host-side clean-up +
+    subdivision + deformation graph, the reference's distance field and Deformer::DeformGraph on the GPU through the
+    C-ABI, host-side LinearSolve; same command line and console lines as the reference binary."""
+    import sys
+    s_obj, t_obj, o_obj = (str(tmp_path / x) for x in ("cad-source.obj", "cad-target.obj", "cad-output.obj"))
+    _write_obj(s_obj, meshes["cadSrcV"], meshes["cadSrcF"]); _write_obj(t_obj, meshes["cadTarV"], meshes["cadTarF"])
+    env = dict(os.environ, MESHODE_PYTHON=sys.executable)
+    p = subprocess.run([_exe("cad_deform"), s_obj, t_obj, o_obj, "64", "5000", "1"], capture_output=True, text=True, timeout=900,
+                       env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    out = p.stdout
+    assert re.search(r"Source:\t\tNum vertices: \d+\tNum faces: \d+", out) and "Reference:\t" in out and out.rstrip().endswith("Deformed")
+    m, first = _costs(out)
+    assert abs(m["Final cost"] - (m["Vertices cost"] + m["Rigidity cost"])) <= 1e-9 * max(m["Final cost"], 1e-30)
+    assert m["Final cost"] < first            # DeformGraph lowered the cost of its problem
+    oV, oF = _read_obj(o_obj)
+    nsub = int(re.search(r"Source:\t\tNum vertices: (\d+)", out).group(1))
+    assert oV.shape[0] == nsub > meshes["cadSrcV"].shape[0] and np.isfinite(oV).all() and oF.max() < oV.shape[0]
+    # the deformed CAD model moved towards the target: mean distance-field value of its vertices decreased
+    from meshode_b200 import pyDeform as pd
+    from meshode_b200 import cadmesh
+    tV, tF = torch.from_numpy(meshes["cadTarV"]).cuda(), torch.from_numpy(meshes["cadTarF"]).cuda()
+    pid = pd.InitializeDeformTemplate(tV, tF, 0, 64)
+    def mean_dist(V):
+        v = torch.from_numpy(np.ascontiguousarray(V, dtype=np.float32)).cuda()
+        pd.NormalizeByTemplate(v, pid)
+        return float(pd.DistanceFieldLoss_forward(v, pid).sqrt().mean())
+    V0 = np.asarray(meshes["cadSrcV"], dtype=np.float64)
+    F0 = cadmesh.remove_degenerated(V0, np.asarray(meshes["cadSrcF"], dtype=np.int64))
+    V0, F0 = cadmesh.merge_duplex(V0, F0)
+    V0, F0 = cadmesh.subdivide(V0, F0, 2e-2)
+    assert V0.shape[0] == nsub
+    assert mean_dist(oV) < 0.8 * mean_dist(V0)
+    pd.DestroyTemplate(pid)
+    # usage line when called without arguments, exit code 0 (cad_deform.cc:22-27)
+    u = subprocess.run([_exe("cad_deform")], capture_output=True, text=True, timeout=60)
+    assert u.returncode == 0 and u.stdout.startswith("./cad_deform cad.obj reference.obj output.obj")
