@@ -71,6 +71,49 @@ def build_apps(force=False):
     return out
 
 
+EXT_DIR = os.path.join(HERE, "ext")
+
+
+def ext_path():
+    import sysconfig
+    return os.path.join(EXT_DIR, "pyDeform" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_ext(force=False, verbose=False):
+    """The compiled ``pyDeform`` module (csrc/pydeform_ext.cpp: pybind11 + libtorch over the C-ABI), in-tree at
+    meshode_b200/ext/pyDeform.<abi>.so -- put that directory on PYTHONPATH to get it as ``import pyDeform``, the
+    way the reference's scripts find their build/ directory.  Compiled with g++ directly (torch's headers, the
+    pybind11 ABI tags of the running torch); libtorch is resolved from the already imported torch at load time,
+    which is the reference's "import torch first" rule (README.md:46-50)."""
+    build_lib()
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+    out = ext_path()
+    src = os.path.join(CSRC, "pydeform_ext.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "meshode_b200.h"), os.path.join(HERE, "..", "apps", "mesh_host.h")]
+    if not (force or _newer(out, deps)):
+        return out
+    os.makedirs(EXT_DIR, exist_ok=True)
+    inc = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    abi = []
+    for name in ("COMPILER_TYPE", "STDLIB", "BUILD_ABI"):
+        val = getattr(torch._C, "_PYBIND11_" + name, None)
+        if val is not None:
+            abi.append('-DPYBIND11_%s="%s"' % (name, val))
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = (["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=pyDeform",
+            "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)] + abi +
+           ["-I" + i for i in inc] + [src, "-o", out, "-L" + tlib, "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10",
+                                      "-lc10_cuda", "-L" + HERE, "-lmeshode_b200", "-Wl,-rpath,$ORIGIN/.."])
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
     print(build_apps(force="--force" in sys.argv))
+    print(build_ext(force="--force" in sys.argv, verbose=True))
