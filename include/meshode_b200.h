@@ -161,7 +161,11 @@ int mo_edges_forward(int param_id, int kind, const float* d_V, int nV, const int
 /* {Rigid,Graph,Cad}EdgeLoss_backward: out float32 [nV,3].  Vertex-gather over the CSR built
  * by mo_edges_store, accumulating each vertex's incident edges in edge order, so the result
  * is bit-identical to the reference's serial scatter loop.  The counts must equal the
- * stored ones (MO_ERR_BAD_ARG otherwise). */
+ * stored ones (MO_ERR_BAD_ARG otherwise).  NOTE: the connectivity is the one captured by
+ * mo_edges_store -- d_F / d_E are only checked for their counts here (the reference walks the
+ * caller's arrays, rigid_layer.cc:113-130; passing a different index array of the same length
+ * than the one stored mixes foreign indices with the stored rest vectors there, a meaningless
+ * result either way).  mo_edges_backward_atomic honours the arrays passed to it. */
 int mo_edges_backward(int param_id, int kind, const float* d_V, int nV, const int* d_F, int nF, const int* d_E,
                       int nE, float* d_grad, mo_stream_t stream);
 /* Same result up to float32 summation order: edge-parallel scatter with warp-aggregated

@@ -641,19 +641,22 @@ int ceres_solve(const Template* TD, int kind, double* d_V, double* d_R, int nV, 
     MO_TRY(fetch(sc + 2, 2));
     const double new_cost = h[0] + h[1];
     const double rho = (cost - new_cost) / model_change;
+    // Ceres' order (TrustRegionMinimizer::Minimize): ParameterToleranceReached (above), then FunctionToleranceReached on
+    // the CANDIDATE whether or not it would be accepted -- the solver returns without applying the step -- then
+    // IsStepSuccessful
+    if (std::fabs(cost - new_cost) <= ftol * cost) { term = 0; break; }
     if (rho > 1e-3) {
       std::swap(x, xn);
       const double t = 2.0 * rho - 1.0;
       radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - t * t * t));
       decrease = 2.0;
-      const double change = cost - new_cost, old = cost;
+      const double change = cost - new_cost;
       MO_TRY(evaluate(x, sc, true));
       MO_TRY(fetch(sc, 5));
       cost = h[0] + h[1]; gmax = h[4];
       ++accepted;
       if (verbose) printf("%4d  %.6e   %9.2e    %.2e   %.2e  %9.2e  %.2e  %7d\n", iter, cost, change, gmax, step_norm, rho, radius, k);
       if (gmax <= gtol) { term = 1; break; }
-      if (std::fabs(change) <= ftol * old) { term = 0; break; }
     } else {
       radius /= decrease; decrease *= 2.0;
       if (verbose) printf("%4d  %.6e   %9.2e    %.2e   %.2e  %9.2e  %.2e  %7d\n", iter, cost, 0.0, gmax, step_norm, rho, radius, k);

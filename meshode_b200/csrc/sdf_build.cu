@@ -45,6 +45,13 @@ constexpr int kThreads = kWarps * 32;
 #endif
 constexpr int kCtasPerSm = MO_SDF_CTAS;
 constexpr int kQueueCap = 8;      // per-lane queue of FP64 candidates
+#ifndef MO_SDF_CHUNK
+#define MO_SDF_CHUNK 8
+#endif
+#ifndef MO_SDF_SUBSPHERE
+#define MO_SDF_SUBSPHERE 1
+#endif
+constexpr int kChunk = MO_SDF_CHUNK;   // triangles whose disc pre-tests run back to back (0: one at a time, vote after each)
 constexpr int kRecParts = 6;      // float4 per triangle record: 4 for the distance test, 2 for the disc bound
 
 // |q_fp32 - q_exact| <= kA * |p-a|^2 + kB for coordinates inside the unit cube: record
@@ -612,12 +619,13 @@ __device__ __forceinline__ void queue_make_room(const SdfArgs& A, const WarpCtx&
 // One cluster against the warp's 32 voxels: per-voxel cylinder test, then the cluster's triangles are staged
 // 32 at a time in the warp's shared memory, pre-tested per voxel with their disc bound and evaluated in FP32
 // only if some lane still needs them.
+// Returns false when no voxel of the block needed the cluster (no bound can have changed).
 template <bool STATS>
-__device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx& w, LaneState& st, const float4 C,
+__device__ __forceinline__ bool process_cluster(const SdfArgs& A, const WarpCtx& w, LaneState& st, const float4 C,
                                                 const float4 Nm, const int2 sc, Counters<STATS>& cn) {
   const bool act = w.valid && !cyl_skip(w.px, w.py, w.pz, st.ub, C, Nm);
   cn.cyl(w.valid ? 1u : 0u);
-  if (!__any_sync(0xffffffffu, act)) return;
+  if (!__any_sync(0xffffffffu, act)) return false;
   for (int tb = 0; tb < sc.y; tb += 32) {
     const int nt = min(32, sc.y - tb);
     __syncwarp();
@@ -628,6 +636,39 @@ __device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx&
     }
     __syncwarp();
     cn.disc(w.valid ? (unsigned)nt : 0u);
+#if MO_SDF_CHUNK > 0
+    // The disc pre-tests run kChunk triangles at a time, branch free: every lane collects a bit mask of the triangles
+    // it still needs, one OR-reduction per chunk tells the warp which of them to evaluate.  While some voxel of the
+    // block has no bound yet (the first cluster of the sweep) the chunk is a single triangle, so that the bound exists
+    // before the bulk of the cluster is pre-tested.
+    for (int j0 = 0; j0 < nt;) {
+      const int lim = __any_sync(0xffffffffu, w.valid && st.ub == __int_as_float(0x7f800000)) ? 1 : min(nt - j0, kChunk);
+      unsigned m = 0u;
+      if (act) {
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)
+          if (!cyl_skip(w.px, w.py, w.pz, st.ub, w.s_tri[4 * 32 + j0 + u], w.s_tri[5 * 32 + j0 + u])) m |= 1u << u;
+      }
+      unsigned todo = __reduce_or_sync(0xffffffffu, m) & ((1u << lim) - 1u);
+      while (todo) {
+        const int j = j0 + __ffs(todo) - 1;
+        todo &= todo - 1u;
+        cn.t32(w.valid ? 1u : 0u);
+        float e;
+        const float q = tri_q(w.s_tri[j], w.s_tri[32 + j], w.s_tri[64 + j], w.s_tri[96 + j], w.px, w.py, w.pz, e);
+        const float qlo = q - e;
+        const bool push = w.valid && qlo <= st.ub;
+        if (__any_sync(0xffffffffu, push && st.cnt == kQueueCap)) queue_make_room(A, w, st, cn);
+        if (push && qlo <= st.ub) {
+          w.s_lid[st.cnt * 32 + w.lane] = sc.x + tb + j;
+          w.s_lq[st.cnt * 32 + w.lane] = qlo;
+          st.cnt++;
+        }
+        st.ub = fminf(st.ub, q + e);
+      }
+      j0 += lim;
+    }
+#else
     for (int j = 0; j < nt; ++j) {
       const bool need = act && !cyl_skip(w.px, w.py, w.pz, st.ub, w.s_tri[4 * 32 + j], w.s_tri[5 * 32 + j]);
       if (!__any_sync(0xffffffffu, need)) continue;
@@ -644,7 +685,9 @@ __device__ __forceinline__ void process_cluster(const SdfArgs& A, const WarpCtx&
       }
       st.ub = fminf(st.ub, q + e);
     }
+#endif
   }
+  return true;
 }
 
 // gap^2 between an AABB stored as ordered uints (lo xyz, hi xyz) and the block's sample box
@@ -728,6 +771,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
   Counters<STATS> cn;
   float ubw = kInf;       // max ub over the block's voxels
   float thr_w = kInf;     // (sqrt(ubw) + Rw)^2
+#if MO_SDF_SUBSPHERE
+  float thr_sub = kInf;   // the same for the lane's 2x2x2 sub-block: (sqrt(max ub of its eight voxels) + Rs)^2
+  const float Rs = (float)(0.8661 * invN * 1.0001);   // half diagonal of a unit-interval sample cube
+  const float sub_off = (float)invN;                  // sub-block centres: (wcx +- 1/N, wcy +- 1/N, wcz)
+#endif
 
   // ---- two-level sweep, nearest first: super cells (4^3 coarse cells) -> coarse cells -> clusters ---------------
   // Every level holds its candidates in registers (two per lane for the 64 children of a node), takes the one with
@@ -767,14 +815,29 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
           const bool has = j < ncl;
           const int cell = cc * 64 + (has ? j : 0);
           unsigned key = 0x7f800000u;
+          float4 C = make_float4(0.f, 0.f, 0.f, 0.f), Nm = C;
           __syncwarp();
           if (has) {
             // the batch lives in the warp's shared memory (registers are needed by the inner loops); every lane keeps
             // only the ordering key of its cluster
-            const float4 C = __ldg(&A.cl_c[cell]), Nm = __ldg(&A.cl_n[cell]);
+            C = __ldg(&A.cl_c[cell]); Nm = __ldg(&A.cl_n[cell]);
             w.s_wc[lane] = C; w.s_wn[lane] = Nm; w.s_wsc[lane] = __ldg(&A.pk_sc[cell]);
             key = __float_as_uint(cyl_lb2(wcx, wcy, wcz, C, Nm));   // ordering only (>= 0: the bit patterns are monotone)
           }
+#if MO_SDF_SUBSPHERE
+          {
+            // A tighter entry test than the block's bounding sphere: the block is four 2x2x2 sub-blocks (bounding
+            // radius 0.87 voxels instead of 2.18), each with the largest running bound of its own eight voxels; a
+            // cluster that every sub-block can skip never reaches the per-voxel test.
+            const float t0 = __shfl_sync(0xffffffffu, thr_sub, 0), t1 = __shfl_sync(0xffffffffu, thr_sub, 2),
+                        t2 = __shfl_sync(0xffffffffu, thr_sub, 8), t3 = __shfl_sync(0xffffffffu, thr_sub, 10);
+            if (key != 0x7f800000u && cyl_skip(wcx - sub_off, wcy - sub_off, wcz, t0, C, Nm) &&
+                cyl_skip(wcx + sub_off, wcy - sub_off, wcz, t1, C, Nm) && cyl_skip(wcx - sub_off, wcy + sub_off, wcz, t2, C, Nm) &&
+                cyl_skip(wcx + sub_off, wcy + sub_off, wcz, t3, C, Nm))
+              key = 0x7f800000u;
+            cn.cyl(has ? 4u : 0u);
+          }
+#endif
           __syncwarp();
           cn.cyl(has ? 2u : 0u);
           bool recheck = true;
@@ -786,7 +849,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
             const float4 fC = w.s_wc[who], fN = w.s_wn[who];
             const int2 fsc = w.s_wsc[who];
             if (lane == who) key = 0x7f800000u;
-            process_cluster(A, w, st, fC, fN, fsc, cn);
+            recheck = false;
+            if (!process_cluster(A, w, st, fC, fN, fsc, cn)) continue;
             const float nub = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(st.ub) : 0u));
             recheck = nub < ubw;
             if (recheck) {
@@ -794,6 +858,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_sdf_tiles(const SdfArg
               const float su = sqrtf(ubw) + Rw;
               thr_w = su * su * 1.00001f;
             }
+#if MO_SDF_SUBSPHERE
+            {   // largest bound of this lane's 2x2x2 sub-block (the lanes that differ in bits 0, 2 and 4)
+              float gm = valid ? st.ub : 0.f;
+              gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 1));
+              gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 4));
+              gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
+              const float su = sqrtf(gm) + Rs;
+              thr_sub = su * su * 1.00001f;
+            }
+#endif
           }
         }
       }

@@ -94,18 +94,19 @@ def solve(grid, kind, V, R, I, rest, lam, max_iterations=100, log=None):
             rho = (cost - new_cost) / model_change
             if log is not None:
                 log.append((summary["iterations"], cost, new_cost, rho, radius))
+            # TrustRegionMinimizer::Minimize order: ParameterToleranceReached (above), FunctionToleranceReached on the
+            # CANDIDATE (accepted or not; the step is not applied), then IsStepSuccessful
+            if abs(cost - new_cost) <= 1e-6 * cost:
+                summary["termination"] = "function tolerance"; break
             if rho > 1e-3:
                 t = 2.0 * rho - 1.0
                 radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - t * t * t)); decrease = 2.0
-                change, old = cost - new_cost, cost
                 x, r, J, cd, ce, cost = xn, rn, Jn, cdn, cen, new_cost
                 g = J.T @ r
                 diag = np.asarray(J.multiply(J).sum(0)).ravel()
                 summary["accepted"] += 1
                 if np.abs(g).max() <= 1e-10:
                     summary["termination"] = "gradient tolerance"; break
-                if abs(change) <= 1e-6 * old:
-                    summary["termination"] = "function tolerance"; break
             else:
                 radius /= decrease; decrease *= 2.0
                 if radius < 1e-32:

@@ -205,8 +205,10 @@ def test_cad_deform_driver_cfg2_pair(tmp_path, meshes):
         v = torch.from_numpy(np.ascontiguousarray(V, dtype=np.float32)).cuda()
         pd.NormalizeByTemplate(v, pid)
         return float(pd.DistanceFieldLoss_forward(v, pid).sqrt().mean())
-    V0 = np.asarray(meshes["cadSrcV"], dtype=np.float64)
-    F0 = cadmesh.remove_degenerated(V0, np.asarray(meshes["cadSrcF"], dtype=np.int64))
+    from meshode_b200.objio import read_obj
+    V0, F0 = read_obj(s_obj, vertex_dtype=np.float64)      # what the driver's host helper read (cad_host.prepare)
+    V0, F0 = np.asarray(V0, dtype=np.float64), np.asarray(F0, dtype=np.int64).reshape(-1, 3)
+    F0 = cadmesh.remove_degenerated(V0, F0)
     V0, F0 = cadmesh.merge_duplex(V0, F0)
     V0, F0 = cadmesh.subdivide(V0, F0, 2e-2)
     assert V0.shape[0] == nsub
