@@ -8,20 +8,24 @@
 //  and cannot be built as a whole here (Eigen, libigl, Ceres,
 // CGAL absent, 3rd_party/* empty).  So:
 //   * PINNED against the reference's own compiled code: both trilinear samplers
-//     (scalar and Jet), DistanceLoss, EdgeLoss, AdaptiveEdgeLoss, EdgeLossWithRot.
-//     oracle/Makefile compiles src/lib/uniformgrid.cc + distanceloss.h + edgeloss.h
-//     where they lie into oracle/_ref/ (against stand-in Eigen/Ceres headers);
-//     tests/test_oracle_ref.py compares bit for bit, tests/golden/golden_ref.npz
-//     carries the same vectors to machines without /root/reference.
+//     (scalar and Jet), DistanceLoss, EdgeLoss, AdaptiveEdgeLoss, EdgeLossWithRot, and
+//     the interface loops of the pyDeform module -- DistanceFieldLoss_forward/backward,
+//     Store{Rigidity,Graph,Cad}Information, {Rigid,Graph,Cad}EdgeLoss_forward/backward,
+//     Normalize/DenormalizeByTemplate.  oracle/Makefile compiles src/lib/uniformgrid.cc +
+//     distanceloss.h + edgeloss.h and src/interface/{distance,rigid,graph,cad}_layer.cc +
+//     normalize.cc where they lie into oracle/_ref/ (against stand-in Eigen / Ceres /
+//     torch::Tensor headers, oracle/stubs/); tests/test_oracle_ref.py compares bit for
+//     bit, tests/golden/golden_ref.npz and golden_iface.npz carry the same vectors to
+//     machines without /root/reference.
 //   * PINNED against torch: the float32 Adam restatement (tests/test_oracle_kat.py).
 //   * PARITY UNPINNED: the libigl nearest-triangle query
 //     (igl::point_mesh_squared_distance @ 7100764c, call site src/lib/mesh.cc:140),
 //     restated as an exact FP64 closest-point search (Ericson, "Real-Time Collision
 //     Detection" 5.1.5, which is what libigl's point_simplex_squared_distance
 //     implements) -- the distance is a unique mathematical quantity, only the index at
-//     exact ties is implementation defined; the interface loops of src/interface/*.cc
-//     (they need torch + pybind11), restated line by line; and, in oracle/lm.py, Ceres'
-//     Levenberg-Marquardt loop (ceres-solver @ d93fac4b).
+//     exact ties is implementation defined; Mesh::Normalize / CopyTensorToMesh (mesh.cc
+//     pulls libigl and CGAL into its translation unit), restated line by line; and, in
+//     oracle/lm.py, Ceres' Levenberg-Marquardt loop (ceres-solver @ d93fac4b).
 //
 // Build: g++ -O2 -ffp-contract=off (the reference's Release flags are -O2,
 // CMakeLists.txt:14; contraction is off so results do not depend on -march).

@@ -26,8 +26,10 @@ def build(force=False):
     """Compiles the reference's sources in place (no-op when /root/reference is absent)."""
     if not os.path.exists(os.path.join(REFERENCE, "src", "lib", "uniformgrid.cc")):
         return SO if os.path.exists(SO) else None
-    if force or not os.path.exists(SO):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REF=" + REFERENCE])
+    stale = os.path.exists(SO) and any(os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(SO)
+                                       for f in ("ref_shim.cc", "ref_iface_shim.cc", "Makefile"))
+    if force or stale or not os.path.exists(SO):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if (force or stale) else "-s", "ref", "REF=" + REFERENCE])
     return SO
 
 
@@ -103,3 +105,70 @@ def edge_rot(p1, p2, rot1, rot2, v, lam):
     r = np.empty(6, np.float64); J = np.empty((6, 12), np.float64)
     lib().ref_edge_rot(_p(p1), _p(p2), _p(rot1), _p(rot2), _p(v), C.c_double(lam), _p(r), _p(J))
     return r, J
+
+
+class Params:
+    """A reference DeformParams (src/interface/deform_params.h:7-25) as InitializeDeformTemplate leaves it -- grid,
+    scale, translation -- driven through the reference's own interface loops (src/interface/*_layer.cc, normalize.cc,
+    compiled where they lie; entry points in oracle/ref_iface_shim.cc)."""
+
+    def __init__(self, grid, scale=1.0, trans=(0.0, 0.0, 0.0)):
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        t = np.ascontiguousarray(trans, dtype=np.float64)
+        self.id = int(lib().ref_params_create(C.c_int(grid.shape[0]), _p(grid), C.c_double(float(scale)), _p(t)))
+
+    @staticmethod
+    def _v(V):
+        V = np.ascontiguousarray(V, dtype=np.float32)
+        assert V.ndim == 2 and V.shape[1] == 3
+        return V
+
+    @staticmethod
+    def _i(I, cols):
+        I = np.ascontiguousarray(I, dtype=np.int32)
+        assert I.ndim == 2 and I.shape[1] == cols
+        return I
+
+    def normalize(self, V, inverse=False):
+        V = self._v(V).copy()
+        lib().ref_iface_normalize(_p(V), C.c_int(V.shape[0]), C.c_int(self.id), C.c_int(int(inverse)))
+        return V
+
+    def dist_forward(self, V):
+        V = self._v(V); out = np.empty(V.shape[0], dtype=np.float32)
+        lib().ref_iface_dist_forward(_p(V), C.c_int(V.shape[0]), C.c_int(self.id), _p(out))
+        return out
+
+    def dist_backward(self, V):
+        V = self._v(V); out = np.empty((V.shape[0], 3), dtype=np.float32)
+        lib().ref_iface_dist_backward(_p(V), C.c_int(V.shape[0]), C.c_int(self.id), _p(out))
+        return out
+
+    def _edges(self, name, V, F, E, rows):
+        V = self._v(V)
+        args = [_p(V), C.c_int(V.shape[0])]
+        if F is not None:
+            F = self._i(F, 3); args += [_p(F), C.c_int(F.shape[0])]
+        if E is not None:
+            E = self._i(E, 2); args += [_p(E), C.c_int(E.shape[0])]
+        args.append(C.c_int(self.id))
+        out = None
+        if rows is not None:
+            out = np.empty((rows, 3), dtype=np.float32); args.append(_p(out))
+        getattr(lib(), name)(*args)
+        return out
+
+    def rigid_store(self, V, F): self._edges("ref_iface_rigid_store", V, F, None, None)
+    def rigid_forward(self, V, F): return self._edges("ref_iface_rigid_forward", V, F, None, 3 * len(F))
+    def rigid_backward(self, V, F): return self._edges("ref_iface_rigid_backward", V, F, None, len(V))
+    def graph_store(self, V, E): self._edges("ref_iface_graph_store", V, None, E, None)
+    def graph_forward(self, V, E): return self._edges("ref_iface_graph_forward", V, None, E, len(E))
+    def graph_backward(self, V, E): return self._edges("ref_iface_graph_backward", V, None, E, len(V))
+    def cad_store(self, V, F, E): self._edges("ref_iface_cad_store", V, F, E, None)
+    def cad_forward(self, V, F, E): return self._edges("ref_iface_cad_forward", V, F, E, len(E) + 3 * len(F))
+    def cad_backward(self, V, F, E): return self._edges("ref_iface_cad_backward", V, F, E, len(V))
+
+    def cad_lambda(self, n):
+        f = lib().ref_iface_cad_lambda
+        f.restype = C.c_float
+        return np.array([f(C.c_int(self.id), C.c_int(i)) for i in range(n)], dtype=np.float32)

@@ -3,6 +3,8 @@
 #ifndef MESHODE_STUB_CERES_JET_
 #define MESHODE_STUB_CERES_JET_
 #include <cmath>
+
+#include <Eigen/Core>   // as the real ceres/jet.h does
 namespace ceres {
 template <typename T, int N>
 struct Jet {
@@ -11,6 +13,13 @@ struct Jet {
   Jet() : a() { for (int i = 0; i < N; ++i) v[i] = T(); }
   explicit Jet(const T& value) : a(value) { for (int i = 0; i < N; ++i) v[i] = T(); }
   Jet(const T& value, int k) : a(value) { for (int i = 0; i < N; ++i) v[i] = T(); v[k] = T(1); }
+  // Jet(a, Eigen::DenseBase<Derived>): scalar part and the N partials given as a vector (src/interface/distance_layer.cc:62-66)
+  template <class S> Jet(const T& value, const Eigen::Matrix<S, N, 1>& vec) : a(value) { for (int i = 0; i < N; ++i) v[i] = T(vec[i]); }
+  // compound operators as in ceres/jet.h: x op= y  is  x = x op y
+  Jet& operator+=(const Jet& y) { *this = *this + y; return *this; }
+  Jet& operator-=(const Jet& y) { *this = *this - y; return *this; }
+  Jet& operator*=(const Jet& y) { *this = *this * y; return *this; }
+  Jet& operator/=(const Jet& y) { *this = *this / y; return *this; }
 };
 #define MESHODE_JET_LOOP for (int i = 0; i < N; ++i)
 template <typename T, int N> inline Jet<T, N> operator+(const Jet<T, N>& f) { return f; }

@@ -273,3 +273,40 @@ def test_fused_loss_matches_layer_composition(cfg1, meshes, golden, oracle, pd):
     lossD = oracle.distfield_forward(golden["grid"], moved) * np.float32(0.5)
     mask = (lossD < np.float32(0.5 * 0.03 * 0.03)).astype(np.float32)[:, None]
     assert np.array_equal(grad2.cpu().numpy(), gD * mask + gR * np.float32(w))
+
+
+def test_interface_entries_match_the_references_own_loops(golden, pd):
+    """The CUDA path against outputs of the REFERENCE's own src/interface/{distance,rigid,graph,cad}_layer.cc and
+    normalize.cc (compiled in place into oracle/_ref, tests/golden/make_golden_iface.py -> golden_iface.npz), with no
+    restatement in between: SURVEY.md s8 rows a11-a16, bit for bit."""
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    from ifacecases import SCALE, TRANS, iface_case
+    from meshode_b200 import capi
+    ref = dict(np.load(os.path.join(gdir, "golden_iface.npz")))
+    V, F, E, moved, raw = iface_case()
+    grid = golden["grid"]
+    N = grid.shape[0]
+    # a template that holds the fixture's field, scale and translation (what InitializeDeformTemplate would leave)
+    tri = _t(np.array([[0.3, 0.3, 0.3], [0.6, 0.3, 0.3], [0.3, 0.6, 0.3]], dtype=np.float64))
+    pid = capi.template_create_normalized(tri.data_ptr(), 3, _t(np.array([[0, 1, 2]], dtype=np.int32)).data_ptr(), 1, N, SCALE, TRANS,
+                                          torch.cuda.current_stream().cuda_stream)
+    pd.SetGrid(pid, _t(grid), _t(grid.astype(np.float32)), _t(np.zeros(grid.shape, dtype=np.int32)))
+    same = lambda t, k: np.array_equal(t.cpu().numpy(), ref[k], equal_nan=True)  # noqa: E731
+    v = _t(raw); pd.NormalizeByTemplate(v, pid); assert same(v, "normalize")
+    v = _t(V); pd.DenormalizeByTemplate(v, pid); assert same(v, "denormalize")
+    dV, dF, dE, dM = _t(V), _t(F), _t(E), _t(moved)
+    assert same(pd.DistanceFieldLoss_forward(dM, pid), "dist_fwd") and same(pd.DistanceFieldLoss_backward(dM, pid), "dist_bwd")
+    pd.StoreRigidityInformation(dV, dF, pid)
+    assert same(pd.RigidEdgeLoss_forward(dM, dF, pid), "rigid_fwd") and same(pd.RigidEdgeLoss_backward(dM, dF, pid), "rigid_bwd")
+    pd.StoreGraphInformation(dV, dE, pid)
+    assert same(pd.GraphEdgeLoss_forward(dM, dE, pid), "graph_fwd") and same(pd.GraphEdgeLoss_backward(dM, dE, pid), "graph_bwd")
+    pd.StoreCadInformation(dV, dF, dE, pid)
+    assert same(pd.CadEdgeLoss_forward(dM, dF, dE, pid), "cad_fwd") and same(pd.CadEdgeLoss_backward(dM, dF, dE, pid), "cad_bwd")
+    # the fused per-iteration entry composes the same two gradients (rigid_loss_layer.py:27)
+    pd.StoreRigidityInformation(dV, dF, pid)
+    _, g = pd.LossForwardBackward(dM, pid, pid, 1.0, 0.0)
+    assert np.array_equal(g.cpu().numpy(), ref["dist_bwd"] + ref["rigid_bwd"])
+    pd.DestroyTemplate(pid)

@@ -94,3 +94,74 @@ def test_live_reference_if_present(oracle, cases):
         lam = float(rng.uniform(0.1, 3))
         assert _same(R.edge_rot(a, b, r1, r2, v, lam)[1], oracle.edge_rot(a, b, r1, r2, v, lam)[1])
         assert R.edge_loss(a, b, v, lam, True)[1] == oracle.edge_loss(a, b, v, lam, True)[1]
+
+
+# ---- the interface loops of the pyDeform module ---------------------------------------
+@pytest.fixture(scope="module")
+def giface():
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_iface.npz")))
+
+
+def _iface_oracle(oracle, grid):
+    """What the oracle computes for the fixture's inputs, keyed like golden_iface.npz."""
+    from ifacecases import SCALE, TRANS, iface_case
+    V, F, E, moved, raw = iface_case()
+    out = {"normalize": oracle.normalize_by_template(raw, SCALE, TRANS),
+           "denormalize": oracle.denormalize_by_template(V, SCALE, TRANS),
+           "dist_fwd": oracle.distfield_forward(grid, moved), "dist_bwd": oracle.distfield_backward(grid, moved)}
+    rest = oracle.store_rigid(V, F)
+    out["rigid_fwd"] = oracle.rigid_forward(moved, F, rest); out["rigid_bwd"] = oracle.rigid_backward(moved, F, rest)
+    rest = oracle.store_graph(V, E)
+    out["graph_fwd"] = oracle.graph_forward(moved, E, rest); out["graph_bwd"] = oracle.graph_backward(moved, E, rest)
+    rest, lam = oracle.store_cad(V, F, E)
+    out["cad_lambda"] = lam
+    out["cad_fwd"] = oracle.cad_forward(moved, F, E, rest, lam); out["cad_bwd"] = oracle.cad_backward(moved, F, E, rest, lam)
+    return out
+
+
+def test_interface_loops_match_reference_golden(oracle, golden, giface):
+    """DistanceFieldLoss_*, {Rigid,Graph,Cad}EdgeLoss_*, Store*Information, Normalize/DenormalizeByTemplate: the oracle's
+    restatement against the outputs of the reference's own src/interface/*.cc (compiled in place), bit for bit."""
+    got = _iface_oracle(oracle, golden["grid"])
+    assert set(got) == set(giface)
+    for k in giface:
+        assert got[k].dtype == giface[k].dtype and _same(got[k], giface[k]), k
+    # the fixture reaches the branches that matter: out-of-bounds penalty, dead band, cut-off, non-trivial lambda
+    from ifacecases import iface_case
+    moved = iface_case()[3]
+    N = golden["grid"].shape[0]
+    idx = np.trunc(moved * N)
+    assert (idx >= N).any() and (idx == N - 1).any() and (moved < 0).any()
+    assert (giface["dist_fwd"] == 0).any() and (giface["dist_fwd"] > 0).any()
+    assert np.unique(giface["cad_lambda"]).size > 100 and np.abs(giface["cad_bwd"]).max() > 0
+
+
+def test_interface_loops_match_reference_live(oracle, golden, giface):
+    from oracle import ref as R
+    if not os.path.exists(os.path.join(R.REFERENCE, "src", "interface", "rigid_layer.cc")):
+        pytest.skip("/root/reference is not present here: covered by golden_iface.npz")
+    from ifacecases import SCALE, TRANS, iface_case
+    R.build()
+    V, F, E, moved, raw = iface_case()
+    P = R.Params(golden["grid"], SCALE, TRANS)
+    assert _same(P.dist_forward(moved), giface["dist_fwd"]) and _same(P.dist_backward(moved), giface["dist_bwd"])
+    # a second, differently seeded case straight against the compiled reference (no fixture in between)
+    rng = np.random.default_rng(99)
+    V2 = (V + rng.normal(0, 0.02, V.shape)).astype(np.float32)
+    mv2 = (V2 + rng.normal(0, 3e-3, V.shape)).astype(np.float32)
+    grid2 = np.abs(rng.normal(0.1, 0.08, golden["grid"].shape))
+    P2 = R.Params(grid2, 0.731, (-0.4, 0.25, 0.05))
+    assert _same(P2.dist_forward(mv2), oracle.distfield_forward(grid2, mv2))
+    assert _same(P2.dist_backward(mv2), oracle.distfield_backward(grid2, mv2))
+    assert _same(P2.normalize(mv2), oracle.normalize_by_template(mv2, 0.731, np.array([-0.4, 0.25, 0.05])))
+    assert _same(P2.normalize(mv2, inverse=True), oracle.denormalize_by_template(mv2, 0.731, np.array([-0.4, 0.25, 0.05])))
+    P2.rigid_store(V2, F); rest = oracle.store_rigid(V2, F)
+    assert _same(P2.rigid_forward(mv2, F), oracle.rigid_forward(mv2, F, rest))
+    assert _same(P2.rigid_backward(mv2, F), oracle.rigid_backward(mv2, F, rest))
+    P2.graph_store(V2, E); rest = oracle.store_graph(V2, E)
+    assert _same(P2.graph_forward(mv2, E), oracle.graph_forward(mv2, E, rest))
+    assert _same(P2.graph_backward(mv2, E), oracle.graph_backward(mv2, E, rest))
+    P2.cad_store(V2, F, E); rest, lam = oracle.store_cad(V2, F, E)
+    assert _same(P2.cad_lambda(lam.shape[0]), lam)
+    assert _same(P2.cad_forward(mv2, F, E), oracle.cad_forward(mv2, F, E, rest, lam))
+    assert _same(P2.cad_backward(mv2, F, E), oracle.cad_backward(mv2, F, E, rest, lam))
