@@ -342,6 +342,32 @@ def percall_block(a, dev, ev):
                     "enqueued from Python; launch-bound, which is why the headline path is one persistent kernel per batch"}
 
 
+def large_block(a, dev, ev):
+    """A source above the 6 144-vertex limit of the one-CTA-per-pair kernel: cfg1's sizes (21 542-vertex source against a
+    14 762-vertex target, grid 64; data/source.obj -> data/target.obj) on synthetic shapes, through mo_deform_adam_large
+    (one cooperative launch for the whole Adam loop)."""
+    import torch
+    from meshode_b200 import engine
+    from meshode_b200.synth import synth_pair
+    nS, nT, iters = 21542, 14762, 2000
+    pair = tuple(torch.from_numpy(x).to(dev) for x in synth_pair(7, nS, nT))
+    ms = []
+    for k in range(2):
+        b = engine.PairBatch([pair], grid_resolution=a.grid, device=dev)
+        e0, e1 = ev(), ev()
+        e0.record()
+        b.deform(iters=iters, lr=1e-3)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+        b.finalize(); b.release()
+    us_it = 1e3 * ms[-1] / iters
+    return {"what": "one pair of cfg1's size (%d-vertex source, %d-vertex target, grid %d): the float32 Adam loop as ONE "
+                    "cooperative launch (k_adam_loop_coop), state in L2" % (nS, nT, a.grid),
+            "us_per_iteration": us_it, "iterations_timed": iters, "pairs_per_s_at_10000_iterations": 1.0 / (us_it * 1e-2),
+            "note": "bit-identical to the CPU loop (tests/test_gpu_deform.py::test_large_mesh_loop_cfg1)"}
+
+
 def slab_block(a, dev, ev, rank, world, barrier):
     """cfg5: ONE 256^3 field on a 500 000-triangle target, built z-sharded over the ranks (cyclic z-tile layers, in-place
     NCCL all-gather), then the GraphLoss2 loss of cad_neural_deform2.py:40-108 on it."""
@@ -576,6 +602,7 @@ def run_b200(a):
         line["fp32_tflops_measured"] = fp32_tf
     if rank == 0 and not a.no_percall:
         line["per_call_path"] = percall_block(a, dev, ev)
+        line["large_mesh_path"] = large_block(a, dev, ev)
 
     # ---- cfg5: one 256^3 field z-sharded over the ranks ------------------------------------------------------
     if world > 1 and not a.no_slab:

@@ -2,7 +2,7 @@ set -u
 mkdir -p gpurun_out
 # 1. SDF variants: timing, then parity of each variant
 rm -f gpurun_out/sdf_bench.log
-for v in default compact compact16; do
+for v in default compact compact16 premask premask_compact pc_ctas2; do
   if [ $v = default ]; then unset MESHODE_B200_LIB; else export MESHODE_B200_LIB=$PWD/build/variants/libmeshode_$v.so; fi
   echo "== $v" >> gpurun_out/sdf_bench.log
   timeout 200 python tools/sdf_bench.py 128 25002 8 >> gpurun_out/sdf_bench.log 2>&1; timeout 100 python tools/sdf_bench.py 64 5000 8 >> gpurun_out/sdf_bench.log 2>&1; timeout 200 python tools/sdf_bench.py 256 250002 4 >> gpurun_out/sdf_bench.log 2>&1
