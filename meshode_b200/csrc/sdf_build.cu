@@ -48,6 +48,9 @@ constexpr int kQueueCap = 8;      // per-lane queue of FP64 candidates
 #ifndef MO_SDF_CHUNK
 #define MO_SDF_CHUNK 8
 #endif
+#ifndef MO_SDF_DIRECTED
+#define MO_SDF_DIRECTED 1
+#endif
 #ifndef MO_SDF_SUBSPHERE
 #define MO_SDF_SUBSPHERE 1
 #endif
@@ -384,11 +387,21 @@ __device__ __forceinline__ bool cyl_skip(const float px, const float py, const f
   const float dc2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
   const float h = fmaf(dz, Nm.z, fmaf(dy, Nm.y, dx * Nm.x));
   const float ah = fmaxf(fabsf(h) - fmaf(4e-7f, dc2, Nm.w), 0.f);
+#if MO_SDF_DIRECTED
+  // the safety margins of the last steps as rounding directions instead of multiplications: A rounded up, S and B
+  // rounded down (every operand is already on its safe side)
+  const float A = __fmaf_ru(-ah, ah, ub);                               // ub - (axial gap)^2, not below the exact value
+  const float t2 = fmaf(-h, h, dc2) - fmaf(1.6e-6f, dc2, 1e-7f);        // lower bound of the squared radial distance
+  const float r2 = C.w * C.w;
+  const float S = __fadd_rd(t2, __fmul_rd(C.w, C.w));
+  const float B = __fsub_rd(S, A);                                      // t2 + rho^2 - A, not above the exact value
+#else
   const float A = fmaf(-0.999999f * ah, ah, ub);                        // ub - (axial gap)^2
   const float t2 = fmaf(-h, h, dc2) - fmaf(1.6e-6f, dc2, 1e-7f);        // lower bound of the squared radial distance
   const float r2 = C.w * C.w;
   const float S = t2 + r2;
   const float B = (S - A) - 4e-7f * (S + fabsf(A));                     // t2 + rho^2 - A, rounded down
+#endif
   // radial gap^2 > A  <=>  t > rho and t2 + rho^2 - A > 2 rho t
   const bool radial = (t2 > r2) && (B > 0.f) && (B * B * 0.99999f > 4.f * r2 * t2);
   return (A < 0.f) || radial;
