@@ -275,7 +275,7 @@ def sdf128_block(a, dev, ev, with_cpu):
                              "%.0f TFLOP/s equivalent), not because it saturates the FMA pipe" %
                              (128 ** 3 * F.shape[0] * 74.0, 128 ** 3 * F.shape[0] * 74.0 / (ms * 1e-3) / 1e12)}}
     if with_cpu:
-        # CPU beside it: the oracle's exact cell-index build of every 8th voxel slice, one slice per host thread,
+        # CPU beside it: the oracle's exact bounding-box-tree build of every 8th voxel slice, one slice per host thread,
         # scaled to the 128 slices (a full build takes ~50 s on 8 cores)
         from oracle import oracle as O
         O.lib()
@@ -299,7 +299,7 @@ def sdf128_block(a, dev, ev, with_cpu):
         wall = time.perf_counter() - t0
         core_s = float(np.sum(t_sl)) * (128 / len(slices))
         blk["cpu_baseline"] = {"value": 1e3 * core_s / cores, "unit": "ms", "cores": cores, "kind": "port",
-                               "sample": "oracle exact cell-index build (stands in for libigl's AABB tree) of voxel slices "
+                               "sample": "oracle exact bounding-box-tree build (libigl's AABB query restated: median-split tree, nearer child first) of voxel slices "
                                          "z = 4, 12, ..., 124 (16 of 128), one slice per host thread, %.1f core-seconds scaled "
                                          "x8 and divided by the %d cores; wall %.1f s" % (float(np.sum(t_sl)), cores, wall)}
     return blk, fp32_tf

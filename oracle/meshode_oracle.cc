@@ -296,8 +296,8 @@ void orc_build_grid_brute(const double* Vn, const int* F, int nF, int N, int z0,
 
 // Same result as orc_build_grid_brute, found with a uniform cell index and a
 // ring search that stops only when no unvisited cell can hold a closer
-// triangle (exact).  This stands in for libigl's AABB tree as the CPU
-// baseline: O(N^3 * local work) instead of O(N^3 * M).
+// triangle (exact).  Kept as a second, independent accelerated builder for the tests; the CPU
+// baseline uses the bounding-box tree below (orc_build_grid_bvh).
 void orc_build_grid_fast(const double* Vn, int nV, const int* F, int nF, int N, int z0, int z1, double* grid, int* idx,
                          int nthreads) {
   (void)nV;
@@ -366,6 +366,106 @@ void orc_build_grid_fast(const double* Vn, int nV, const int* F, int nF, int N, 
           // Chebyshev distance >= r+1, i.e. at Euclidean distance >= r*cs
           const double lb = r * cs;
           if (bi >= 0 && best <= lb * lb) break;
+        }
+        const size_t o = ((size_t)i * N + j) * N + k;
+        grid[o] = std::sqrt(best);
+        if (idx) idx[o] = bi;
+      }
+  });
+}
+
+// Same result again, found the way libigl finds it (igl::AABB<...,3>::squared_distance behind
+// igl::point_mesh_squared_distance, src/lib/mesh.cc:140; libigl is un-vendored, restated from its
+// published algorithm): a bounding-box tree over the triangles, split at the median centroid of the
+// longest axis, queried depth first with the nearer child first and a subtree skipped when the
+// squared distance from the query point to its box exceeds the best distance found so far.  This is
+// the CPU baseline's builder: O(log M)-ish work per voxel wherever the voxel lies, where the ring
+// search above degenerates to most of the mesh for voxels far from the surface.
+// Exactness: a subtree is skipped only if its box bound exceeds the running best by more than the
+// rounding of either number can explain (relative 1e-9), so every triangle that could win or tie
+// is evaluated with point_triangle_sqr; ties go to the lowest index as in the brute-force loop.
+namespace {
+struct BvhNode { double lo[3], hi[3]; int left, right, start, count; };
+struct Bvh {
+  std::vector<BvhNode> nodes;
+  std::vector<int> order;   // triangle indices, leaf ranges contiguous
+};
+int bvh_build(Bvh& T, const double* cen, const double* tlo, const double* thi, int start, int count) {
+  const int id = (int)T.nodes.size();
+  T.nodes.emplace_back();
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+  for (int i = start; i < start + count; ++i) {
+    const int t = T.order[i];
+    for (int j = 0; j < 3; ++j) {
+      lo[j] = std::min(lo[j], tlo[3 * t + j]); hi[j] = std::max(hi[j], thi[3 * t + j]);
+      clo[j] = std::min(clo[j], cen[3 * t + j]); chi[j] = std::max(chi[j], cen[3 * t + j]);
+    }
+  }
+  int axis = 0;
+  for (int j = 1; j < 3; ++j) if (chi[j] - clo[j] > chi[axis] - clo[axis]) axis = j;
+  int left = -1, right = -1;
+  if (count > 4 && chi[axis] > clo[axis]) {
+    const int mid = start + count / 2;
+    std::nth_element(T.order.begin() + start, T.order.begin() + mid, T.order.begin() + start + count,
+                     [&](int a, int b) { return cen[3 * a + axis] < cen[3 * b + axis] || (cen[3 * a + axis] == cen[3 * b + axis] && a < b); });
+    left = bvh_build(T, cen, tlo, thi, start, mid - start);
+    right = bvh_build(T, cen, tlo, thi, mid, start + count - mid);
+  }
+  BvhNode& n = T.nodes[id];
+  for (int j = 0; j < 3; ++j) { n.lo[j] = lo[j]; n.hi[j] = hi[j]; }
+  n.left = left; n.right = right; n.start = start; n.count = count;
+  return id;
+}
+inline double box_dist2(const BvhNode& n, const double* p) {
+  double d2 = 0;
+  for (int j = 0; j < 3; ++j) {
+    const double g = std::max(0.0, std::max(n.lo[j] - p[j], p[j] - n.hi[j]));
+    d2 += g * g;
+  }
+  return d2;
+}
+}  // namespace
+
+void orc_build_grid_bvh(const double* Vn, int nV, const int* F, int nF, int N, int z0, int z1, double* grid, int* idx,
+                        int nthreads) {
+  (void)nV;
+  Bvh T;
+  std::vector<double> cen(3 * (size_t)std::max(nF, 1)), tlo(3 * (size_t)std::max(nF, 1)), thi(3 * (size_t)std::max(nF, 1));
+  T.order.resize((size_t)nF);
+  for (int t = 0; t < nF; ++t) {
+    T.order[t] = t;
+    for (int j = 0; j < 3; ++j) {
+      const double a = Vn[3 * F[3 * t] + j], b = Vn[3 * F[3 * t + 1] + j], c = Vn[3 * F[3 * t + 2] + j];
+      tlo[3 * t + j] = std::min(a, std::min(b, c)); thi[3 * t + j] = std::max(a, std::max(b, c));
+      cen[3 * t + j] = (a + b + c) / 3.0;
+    }
+  }
+  if (nF > 0) { T.nodes.reserve(2 * (size_t)nF); bvh_build(T, cen.data(), tlo.data(), thi.data(), 0, nF); }
+  parallel_slices(z0, z1, nthreads, [&](int i) {
+    std::vector<int> stack;
+    stack.reserve(128);
+    for (int j = 0; j < N; ++j)
+      for (int k = 0; k < N; ++k) {
+        const double p[3] = {double(k) / N, double(j) / N, double(i) / N};
+        double best = std::numeric_limits<double>::infinity();
+        int bi = -1;
+        stack.clear();
+        if (nF > 0) stack.push_back(0);
+        while (!stack.empty()) {
+          const BvhNode& n = T.nodes[stack.back()];
+          stack.pop_back();
+          if (box_dist2(n, p) > best * (1.0 + 1e-9) + 1e-300) continue;
+          if (n.left < 0) {
+            for (int s2 = n.start; s2 < n.start + n.count; ++s2) {
+              const int t = T.order[s2];
+              const double d = point_triangle_sqr(p, Vn + 3 * F[3 * t], Vn + 3 * F[3 * t + 1], Vn + 3 * F[3 * t + 2], nullptr);
+              if (d < best || (d == best && t < bi)) { best = d; bi = t; }
+            }
+          } else {
+            const double dl = box_dist2(T.nodes[n.left], p), dr = box_dist2(T.nodes[n.right], p);
+            if (dl <= dr) { stack.push_back(n.right); stack.push_back(n.left); }   // nearer child on top
+            else { stack.push_back(n.left); stack.push_back(n.right); }
+          }
         }
         const size_t o = ((size_t)i * N + j) * N + k;
         grid[o] = std::sqrt(best);
@@ -672,7 +772,7 @@ void orc_deform_pair(const float* tarV, int nTv, const int* tarF, int nTf, float
   std::vector<double> Vn(3 * (size_t)nTv), grid((size_t)N * N * N);
   double scale, pos[3];
   orc_normalize_target(tarV, nTv, Vn.data(), &scale, pos);
-  orc_build_grid_fast(Vn.data(), nTv, tarF, nTf, N, 0, N, grid.data(), nullptr, build_threads);
+  orc_build_grid_bvh(Vn.data(), nTv, tarF, nTf, N, 0, N, grid.data(), nullptr, build_threads);
   orc_normalize_by_template(srcV, nSv, scale, pos);
   std::vector<float> rest(9 * (size_t)nSf);
   orc_store_rigid(srcV, srcF, nSf, rest.data());

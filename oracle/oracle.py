@@ -69,7 +69,9 @@ def point_triangle_sqr(p, a, b, c):
 
 
 def build_grid(Vn, F, N, z0=0, z1=None, fast=True, threads=None, want_idx=True):
-    """FP64 distance grid [z][y][x] and nearest-triangle index (mesh.cc:106-152)."""
+    """FP64 distance grid [z][y][x] and nearest-triangle index (mesh.cc:106-152).  ``fast``: True / "bvh" = bounding-box
+    tree (what libigl's query does; the CPU baseline), "cells" = uniform cell index with a ring search, False = brute
+    force over all triangles (the ground truth the other two are checked against).  Same result from all three."""
     Vn = _c(Vn, _f64)
     F = _c(F, _i32)
     z1 = N if z1 is None else z1
@@ -77,7 +79,10 @@ def build_grid(Vn, F, N, z0=0, z1=None, fast=True, threads=None, want_idx=True):
     grid = np.full((N, N, N), 1e30, _f64)  # uniformgrid.cc:9-17 initial value
     idx = np.full((N, N, N), -1, _i32) if want_idx else None
     ip = _p(idx) if want_idx else None
-    if fast:
+    if fast is True or fast == "bvh":
+        lib().orc_build_grid_bvh(_p(Vn), C.c_int(Vn.shape[0]), _p(F), C.c_int(F.shape[0]), C.c_int(N), C.c_int(z0),
+                                 C.c_int(z1), _p(grid), ip, C.c_int(threads))
+    elif fast == "cells":
         lib().orc_build_grid_fast(_p(Vn), C.c_int(Vn.shape[0]), _p(F), C.c_int(F.shape[0]), C.c_int(N), C.c_int(z0),
                                   C.c_int(z1), _p(grid), ip, C.c_int(threads))
     else:

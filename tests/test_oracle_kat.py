@@ -111,20 +111,32 @@ def test_grid_layout_single_triangle(oracle):
 
 
 def test_grid_fast_equals_brute(oracle, meshes):
+    """Both accelerated CPU builders -- the bounding-box tree (libigl's AABB query restated; the CPU baseline) and the
+    uniform cell index with a ring search -- return the brute-force field and index bit for bit, ties included."""
     rng = np.random.default_rng(1)
     Vn, _, _ = oracle.normalize_target(meshes["cadTarV"])
     F = meshes["cadTarF"]
     for N in (7, 16):
         gb, ib = oracle.build_grid(Vn, F, N, fast=False)
-        gf, if_ = oracle.build_grid(Vn, F, N, fast=True)
-        assert np.array_equal(gb, gf) and np.array_equal(ib, if_)
-    # random soup with triangles sticking out of the unit cube, slab build
+        for mode in ("bvh", "cells"):
+            gf, if_ = oracle.build_grid(Vn, F, N, fast=mode)
+            assert np.array_equal(gb, gf) and np.array_equal(ib, if_), (N, mode)
+    # random soup with triangles sticking out of the unit cube (plus exact duplicates: ties), slab build
     V = rng.uniform(-0.2, 1.2, size=(300, 3)); F = rng.integers(0, 300, size=(500, 3)).astype(np.int32)
+    F = np.concatenate([F, F[:40]])
     gb, ib = oracle.build_grid(V, F, 12, fast=False)
-    gf, if_ = oracle.build_grid(V, F, 12, fast=True)
-    assert np.array_equal(gb, gf) and np.array_equal(ib, if_)
-    gs, _ = oracle.build_grid(V, F, 12, z0=3, z1=7, fast=True)
-    assert np.array_equal(gs[3:7], gb[3:7]) and (gs[:3] == 1e30).all() and (gs[7:] == 1e30).all()
+    for mode in (True, "cells"):
+        gf, if_ = oracle.build_grid(V, F, 12, fast=mode)
+        assert np.array_equal(gb, gf) and np.array_equal(ib, if_), mode
+        gs, _ = oracle.build_grid(V, F, 12, z0=3, z1=7, fast=mode)
+        assert np.array_equal(gs[3:7], gb[3:7]) and (gs[:3] == 1e30).all() and (gs[7:] == 1e30).all()
+    # the two accelerated builders against each other at a size brute force would take minutes for
+    from meshode_b200.synth import synth_mesh
+    Vs, Fs = synth_mesh(2000, 5)
+    Vsn, _, _ = oracle.normalize_target(Vs)
+    g1, i1 = oracle.build_grid(Vsn, Fs, 40, fast="bvh")
+    g2, i2 = oracle.build_grid(Vsn, Fs, 40, fast="cells")
+    assert np.array_equal(g1, g2) and np.array_equal(i1, i2)
 
 
 def test_grid_matches_golden(oracle, meshes, golden):
