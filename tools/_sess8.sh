@@ -1,7 +1,6 @@
 set -u
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/smi8.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_multi.py -q -m gpu -rA > gpurun_out/pytest_multi.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi.log; tail -6 gpurun_out/pytest_multi.log
-for n in 8 2; do
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 2 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; echo "bench n=$n exit $?"; cut -c1-600 gpurun_out/bench_n$n.json; tail -5 gpurun_out/bench_n$n.err
+timeout 600 python -m pytest tests/test_gpu_multi.py -q -m gpu -rA > gpurun_out/pytest_multi.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi.log; tail -4 gpurun_out/pytest_multi.log
+for n in 8 4 2; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 2 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; echo "bench n=$n exit $?"; grep '^{' gpurun_out/bench_n$n.json | cut -c1-200; tail -3 gpurun_out/bench_n$n.err
 done
