@@ -186,3 +186,32 @@ def test_fast_and_exact_agree_over_a_few_iterations(oracle, pd):
     # Adam's first steps are +-lr per coordinate; a gradient at the sign threshold may flip one of them
     assert (d <= 1e-6).float().mean().item() > 0.995 and d.max().item() <= 6.1e-3
     a.release(); b.release()
+
+
+@pytest.mark.parametrize("schedule", ["cta", "cluster"])
+@pytest.mark.parametrize("fan", [1, 9, 26])
+def test_hub_vertices_take_the_long_adjacency_rows(oracle, pd, fan, schedule):
+    """A vertex with many incident edges: 2*fan + its own ~12 incidences exceed the eight adjacency words that the loop
+    reads with vector loads (fan = 1: exactly eight words; 9: eight more rows; 26: many), so the remaining rows come from
+    the row-major table.  Same bits as the CPU loop on both schedules, in a batch next to an ordinary pair."""
+    from meshode_b200 import engine
+    from meshode_b200.synth import synth_pair
+    srcV, srcF, tarV, tarF = synth_pair(31, 1100, 900)
+    rng = np.random.default_rng(fan)
+    hub, ring = 17, rng.choice(np.arange(100, 1100), size=max(fan, 2), replace=False)
+    extra = np.stack([np.full(ring.size, hub), ring, np.roll(ring, 1)], 1).astype(np.int32)[:fan]   # a fan of triangles around the hub
+    srcF2 = np.ascontiguousarray(np.concatenate([srcF[:900], extra, srcF[900:]]))        # in the middle of the edge order
+    deg = np.bincount(srcF2.reshape(-1), minlength=srcV.shape[0])
+    assert 2 * deg[hub] == {1: 16, 9: 32, 26: 66}[fan]   # exactly eight words; one table row beyond them; many
+    other = synth_pair(32, 1000, 900)
+    pairs = [(srcV, srcF2, tarV, tarF), other]
+    batch = engine.PairBatch([tuple(torch.from_numpy(a) for a in p) for p in pairs], grid_resolution=32)
+    iters = 80
+    batch.deform(iters=iters, lr=1e-3, exact=True, schedule=schedule)
+    for k, (sV, sF, tV, tF) in enumerate(pairs):
+        tmpl = oracle.Template(tV, tF, 32)
+        src_n = oracle.normalize_by_template(sV, tmpl.scale, tmpl.trans)
+        ref, _ = oracle.rigid_adam(tmpl.grid, src_n, sF, oracle.store_rigid(src_n, sF), iters, 1e-3)
+        got = batch.V[k].cpu().numpy()
+        assert np.array_equal(got, ref), "pair %d: max |dV| = %g" % (k, np.abs(got - ref).max())
+    batch.release()
