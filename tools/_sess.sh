@@ -1,3 +1,3 @@
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_deform.py -q -m gpu -rA 2>&1 | tail -30 | cut -c1-200
+build/f32x2_probe > gpurun_out/f32x2_probe.log 2>&1; cat gpurun_out/f32x2_probe.log
