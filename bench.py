@@ -238,6 +238,15 @@ def sdf128_block(a, dev, ev, with_cpu):
     f1.record()
     torch.cuda.synchronize()
     fp32_tf = 148 * 8 * 256 * it_f * 8 * 2 / (f0.elapsed_time(f1) * 1e-3) / 1e12
+    # the same chain on packed operands (FFMA2): the larger of the two is the denominator
+    capi.check(capi.lib().mo_microbench_fp32x2(148 * 8, 256, it_f // 2, sink.data_ptr(), s))
+    f2, f3 = ev(), ev()
+    f2.record()
+    capi.check(capi.lib().mo_microbench_fp32x2(148 * 8, 256, it_f // 2, sink.data_ptr(), s))
+    f3.record()
+    torch.cuda.synchronize()
+    fp32x2_tf = 148 * 8 * 256 * (it_f // 2) * 8 * 4 / (f2.elapsed_time(f3) * 1e-3) / 1e12
+    fp32_scalar_tf, fp32_tf = fp32_tf, max(fp32_tf, fp32x2_tf)
     times, stats = [], None
     for k in range(3 + 5):
         b0, b1 = ev(), ev()
@@ -266,7 +275,8 @@ def sdf128_block(a, dev, ev, with_cpu):
         "fp64_tests": stats["fp64_tests"],
         "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": tf / fp32_tf,
                      "fp32_frac_tests_only": tf_tests / fp32_tf, "traffic": None,
-                     "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 "
+                     "peak_scalar_ffma": fp32_scalar_tf, "peak_packed_ffma2": fp32x2_tf,
+                     "peak_source": "FFMA / FFMA2-chain microbenchmarks measured in this run, the larger (MEASURED_PEAKS.json has no FP32 "
                                     "entry); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                      "note": "achieved = (point-triangle tests executed x 74 + bounding-cylinder tests of clusters and "
                              "bounding-disc pre-tests of triangles x 38 FLOP, all counted by the kernel) / build time "

@@ -42,6 +42,9 @@ unsigned long long mo_launch_count(void);
  * dependent-free FMA groups (8 independent chains); flops = blocks*threads*iters*8*2.
  * d_sink (>= blocks*threads floats) keeps the result alive. */
 int mo_microbench_fp32(int blocks, int threads, int iters, float* d_sink, mo_stream_t stream);
+/* The same on packed operands (fma.rn.f32x2, two FMAs per instruction): flops = blocks*threads*iters*8*4.
+ * sm_100 issues it at half rate, so it lands a few per cent above the scalar chain; bench.py takes the larger. */
+int mo_microbench_fp32x2(int blocks, int threads, int iters, float* d_sink, mo_stream_t stream);
 /* number of visible CUDA devices (0 when there is none). */
 int mo_device_count(void);
 

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mo_launch_count": [],
     "mo_build_stats_enable": [_i],
     "mo_microbench_fp32": [_i, _i, _i, _vp, _vp],
+    "mo_microbench_fp32x2": [_i, _i, _i, _vp, _vp],
     "mo_template_create": [_vp, _i, _vp, _i, _i, _i, _vp, _ip],
     "mo_template_create_slab": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _ip],
     "mo_template_create_layers": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _ip],

@@ -1,3 +1,8 @@
 set -u
 mkdir -p gpurun_out
-build/f32x2_probe > gpurun_out/f32x2_probe.log 2>&1; cat gpurun_out/f32x2_probe.log
+timeout 600 python bench.py --pairs 148 --iters 500 --steps 1 --warmup 3 --no-cpu > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err; echo "exit $?"; python - <<'P'
+import json
+d=json.load(open('gpurun_out/bench_small.json'))
+print(d['value'], d['sdf_build_128']['value'], d['sdf_build_128']['roofline'])
+P
+tail -3 gpurun_out/bench_small.err
