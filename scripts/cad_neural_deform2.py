@@ -30,6 +30,8 @@ parser.add_argument('--resume_path', default='')
 args = parser.parse_args()
 
 rigidity = float(args.rigidity)
+if os.environ.get('MESHODE_SEED'):   # (additive: a fixed initialisation of the flow for tests; the reference draws it unseeded)
+    torch.manual_seed(int(os.environ['MESHODE_SEED']))
 device = torch.device(args.device)
 if device.type != 'cuda':
     raise SystemExit('meshode_b200 runs on a CUDA device (no CPU fallback)')
