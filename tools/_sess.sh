@@ -1,11 +1,11 @@
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
-export MESHODE_EXACT=1 MESHODE_SCHEDULE=cta
-timeout 120 python tools/deform_bench.py 148 400 5000
-timeout 120 python tools/deform_bench.py 148 400 5000
-unset MESHODE_EXACT MESHODE_SCHEDULE
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_deform_adam -c 2 -f \
-    -o gpurun_out/prof_deform_v10 python tools/prof_target.py deform 157 300 > gpurun_out/ncu_deform_v10.log 2>&1
-timeout 400 compute-sanitizer --tool memcheck python tools/sanitize_target.py > gpurun_out/sanitize_memcheck_v10.log 2>&1; tail -4 gpurun_out/sanitize_memcheck_v10.log
+timeout 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/bench_n1.json'))
+print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['launch_ms'], d['roofline']['share_of_step'], d['cpu_baseline']['value'], d['clocks'])
+print(d['sdf_build_128']['value'], d['per_call_path']['us_per_iteration'], d['large_mesh_path']['us_per_iteration'])
+P
+tail -3 gpurun_out/bench_n1.err
+timeout 600 python -m pytest tests/test_gpu_apps.py -x -q 2>&1 | tail -3
