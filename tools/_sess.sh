@@ -1,11 +1,12 @@
 set -u
 mkdir -p gpurun_out
-timeout 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
-python - <<'P'
-import json
-d=json.load(open('gpurun_out/bench_n1.json'))
-print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['launch_ms'], d['roofline']['share_of_step'], d['cpu_baseline']['value'], d['clocks'])
-print(d['sdf_build_128']['value'], d['per_call_path']['us_per_iteration'], d['large_mesh_path']['us_per_iteration'])
-P
-tail -3 gpurun_out/bench_n1.err
-timeout 600 python -m pytest tests/test_gpu_apps.py -x -q 2>&1 | tail -3
+export MESHODE_EXACT=1
+MESHODE_SCHEDULE=cluster timeout 120 python tools/deform_bench.py 9 400 5000
+MESHODE_SCHEDULE=cluster timeout 120 python tools/deform_bench.py 29 400 5000
+MESHODE_SCHEDULE=cluster timeout 120 python tools/deform_bench.py 1 400 5000
+MESHODE_SCHEDULE=auto timeout 120 python tools/deform_bench.py 157 400 5000
+MESHODE_SCHEDULE=auto timeout 120 python tools/deform_bench.py 453 400 5000
+MESHODE_SCHEDULE=cta timeout 120 python tools/deform_bench.py 453 400 5000
+unset MESHODE_EXACT
+timeout 600 python -m pytest tests/test_gpu_deform.py -x -q 2>&1 | tail -5
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
