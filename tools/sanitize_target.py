@@ -14,7 +14,8 @@ from meshode_b200.synth import synth_pair  # noqa: E402
 dev = "cuda:0"
 pairs = [tuple(torch.from_numpy(a) for a in synth_pair(i, 700 + 300 * i, 600)) for i in range(3)]
 b = engine.PairBatch(pairs, 32, device=dev)
-b.deform(iters=25)                      # fused exact loop (records, staging, repeat flags)
+b.deform(iters=25, schedule="cta")      # fused exact loop, one CTA per pair (tensor-memory records, repeat flags)
+b.deform(iters=25, schedule="cluster")  # the same loop on thread-block clusters (double-buffered replicas over DSMEM)
 b.deform(iters=5, exact=False)          # fast loop
 V = b.finalize()
 b.release()
