@@ -1,5 +1,4 @@
 set -u
 mkdir -p gpurun_out
-MESHODE_B200_LIB=build/variants/libmeshode_cluster_notmem.so timeout 300 compute-sanitizer --tool racecheck python tools/sanitize_mini.py cluster > gpurun_out/sanitize_racecheck_cluster_notmem.log 2>&1; echo "exit $?"; grep -v "Host Frame" gpurun_out/sanitize_racecheck_cluster_notmem.log | tail -8
-MESHODE_B200_LIB=build/variants/libmeshode_cluster_notmem.so timeout 300 compute-sanitizer --tool synccheck python tools/sanitize_mini.py cluster > gpurun_out/sanitize_synccheck_cluster_notmem.log 2>&1; echo "exit $?"; grep -v "Host Frame" gpurun_out/sanitize_synccheck_cluster_notmem.log | tail -4
-MESHODE_B200_LIB=build/variants/libmeshode_cluster_notmem.so timeout 300 python -m pytest tests/test_gpu_deform.py -q -k "cluster or partial" 2>&1 | tail -3
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_bench_v10.csv python bench.py --steps 1 --warmup 1 --pairs 148 --iters 1000 --no-cpu --no-sdf128 --no-percall > gpurun_out/launches_bench_v10.log 2>&1; echo "exit $?"
+tail -2 gpurun_out/launches_bench_v10.log | cut -c1-300
