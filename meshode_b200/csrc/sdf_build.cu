@@ -218,6 +218,9 @@ __device__ __forceinline__ void cyl_extent(const double* v, const float cf[3], c
 }
 __device__ __forceinline__ float pad_tau(double max_h) { return __double2float_ru(max_h * 1.000001 + 4e-7); }
 __device__ __forceinline__ float pad_rho(double max_t2) { return __double2float_ru(sqrt(fmax(max_t2, 0.0)) * 1.000001 + 2e-7); }
+// The records store rho^2, rounded up: the bound is then the cylinder of radius sqrt(stored value) >= rho, for which the
+// stored number is exact -- cyl_skip needs no squaring and no rounding margin for it.
+__device__ __forceinline__ float pad_rho2(double max_t2) { const float r = pad_rho(max_t2); return __fmul_ru(r, r); }
 
 __global__ void k_tri_fill(const double* __restrict__ Vn, const int* __restrict__ F, int nF,
                            const int* __restrict__ tri_cell, const int2* __restrict__ cl_sc,
@@ -274,7 +277,7 @@ __global__ void k_tri_fill(const double* __restrict__ Vn, const int* __restrict_
     if (!(fabsf(nf[0]) + fabsf(nf[1]) + fabsf(nf[2]) > 0.5f)) { nf[0] = 0.f; nf[1] = 0.f; nf[2] = 1.f; }
     double mh = 0.0, mt2 = 0.0;
     cyl_extent(a, cf, nf, mh, mt2); cyl_extent(b, cf, nf, mh, mt2); cyl_extent(cc, cf, nf, mh, mt2);
-    r[4] = make_float4(cf[0], cf[1], cf[2], pad_rho(mt2));
+    r[4] = make_float4(cf[0], cf[1], cf[2], pad_rho2(mt2));
     r[5] = make_float4(nf[0], nf[1], nf[2], pad_tau(mh));
   }
   tri_id[slot] = t;
@@ -333,7 +336,7 @@ __global__ void k_cluster(const int2* __restrict__ cl_sc, int ncell, const doubl
   }
   mh = warp_max_d(mh); mt2 = warp_max_d(mt2);
   if (lane == 0) {
-    cl_c[slot] = make_float4(cf[0], cf[1], cf[2], pad_rho(mt2));
+    cl_c[slot] = make_float4(cf[0], cf[1], cf[2], pad_rho2(mt2));
     cl_n[slot] = make_float4(nf[0], nf[1], nf[2], pad_tau(mh));
     pk_sc[slot] = sc;
   }
@@ -372,7 +375,7 @@ __global__ void k_super(const int* __restrict__ coarse_ncl, const unsigned* __re
 
 // ---------------------------------------------------------------------------------
 // Cylinder bound.  A cluster (or a single triangle) lies inside the cylinder
-//   { x : |(x-c).n| <= tau,  |(x-c) - ((x-c).n) n| <= rho }      (n unit, c = C.xyz, rho = C.w, tau = Nm.w)
+//   { x : |(x-c).n| <= tau,  |(x-c) - ((x-c).n) n| <= rho }      (n unit, c = C.xyz, rho^2 = C.w, tau = Nm.w)
 // so dist(p, cluster)^2 >= max(|h|-tau, 0)^2 + max(t-rho, 0)^2 with h = (p-c).n, t^2 = |p-c|^2 - h^2.
 // cyl_skip returns true only if that lower bound exceeds ub, evaluated in FP32 without a square
 // root and with every rounding on the safe side for coordinates inside the unit cube:
@@ -389,21 +392,21 @@ __device__ __forceinline__ bool cyl_skip(const float px, const float py, const f
   const float ah = fmaxf(fabsf(h) - fmaf(4e-7f, dc2, Nm.w), 0.f);
 #if MO_SDF_DIRECTED
   // the safety margins of the last steps as rounding directions instead of multiplications: A rounded up, S and B
-  // rounded down (every operand is already on its safe side)
+  // rounded down (every operand is already on its safe side; r2 = rho^2 is exact by construction, see pad_rho2)
   const float A = __fmaf_ru(-ah, ah, ub);                               // ub - (axial gap)^2, not below the exact value
   const float t2 = fmaf(-h, h, dc2) - fmaf(1.6e-6f, dc2, 1e-7f);        // lower bound of the squared radial distance
-  const float r2 = C.w * C.w;
-  const float S = __fadd_rd(t2, __fmul_rd(C.w, C.w));
+  const float r2 = C.w;
+  const float S = __fadd_rd(t2, r2);
   const float B = __fsub_rd(S, A);                                      // t2 + rho^2 - A, not above the exact value
 #else
   const float A = fmaf(-0.999999f * ah, ah, ub);                        // ub - (axial gap)^2
   const float t2 = fmaf(-h, h, dc2) - fmaf(1.6e-6f, dc2, 1e-7f);        // lower bound of the squared radial distance
-  const float r2 = C.w * C.w;
+  const float r2 = C.w;
   const float S = t2 + r2;
   const float B = (S - A) - 4e-7f * (S + fabsf(A));                     // t2 + rho^2 - A, rounded down
 #endif
-  // radial gap^2 > A  <=>  t > rho and t2 + rho^2 - A > 2 rho t
-  const bool radial = (t2 > r2) && (B > 0.f) && (B * B * 0.99999f > 4.f * r2 * t2);
+  // radial gap^2 > A  <=>  t > rho and t2 + rho^2 - A > 2 rho t   (both sides of the squared form scaled by 1/4: exact)
+  const bool radial = (t2 > r2) && (B > 0.f) && (B * B * (0.25f * 0.99999f) > r2 * t2);
   return (A < 0.f) || radial;
 }
 // the same bound as a number (ordering only, not rigorous)
@@ -412,7 +415,7 @@ __device__ __forceinline__ float cyl_lb2(const float px, const float py, const f
   const float dc2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
   const float h = fmaf(dz, Nm.z, fmaf(dy, Nm.y, dx * Nm.x));
   const float ah = fmaxf(fabsf(h) - Nm.w, 0.f);
-  const float tg = fmaxf(sqrtf(fmaxf(fmaf(-h, h, dc2), 0.f)) - C.w, 0.f);
+  const float tg = fmaxf(sqrtf(fmaxf(fmaf(-h, h, dc2), 0.f)) - sqrtf(C.w), 0.f);
   return fmaf(ah, ah, tg * tg);
 }
 
@@ -454,7 +457,9 @@ __device__ __forceinline__ float tri_q(const float4 r0, const float4 r1, const f
     q = inside ? qf : qe;
   } else {
     q = qe;
-    err = fmaf(-2.f * r3.x, sqrtf(fmaxf(qe, 0.f)), err);
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaxf(qe, 0.f)));   // (an upper bound is all that is needed: 2 ulp + margin)
+    err = fmaf(-2.f * r3.x, sq * 1.000001f + 1e-30f, err);
   }
   return fmaxf(q, 0.f);
 }

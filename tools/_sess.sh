@@ -1,4 +1,7 @@
 set -u
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_bench_v10.csv python bench.py --steps 1 --warmup 1 --pairs 148 --iters 1000 --no-cpu --no-sdf128 --no-percall > gpurun_out/launches_bench_v10.log 2>&1; echo "exit $?"
-tail -2 gpurun_out/launches_bench_v10.log | cut -c1-300
+for rep in 1 2; do
+echo "== old"; for c in "128 25002" "64 5000" "256 250002"; do MESHODE_B200_LIB=build/variants/libmeshode_sdfold.so timeout 120 python tools/sdf_bench.py $c 6; done
+echo "== new"; for c in "128 25002" "64 5000" "256 250002"; do timeout 120 python tools/sdf_bench.py $c 6; done
+done
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -3
