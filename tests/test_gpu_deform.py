@@ -215,3 +215,43 @@ def test_hub_vertices_take_the_long_adjacency_rows(oracle, pd, fan, schedule):
         got = batch.V[k].cpu().numpy()
         assert np.array_equal(got, ref), "pair %d: max |dV| = %g" % (k, np.abs(got - ref).max())
     batch.release()
+
+
+def _grid_mesh(m, n, closed):
+    """m x n vertices on a torus (closed: every vertex has 12 incident edge slots) or on a bent open patch (boundary
+    vertices have as few as 4, so the adjacency rows are padded from the third word on)."""
+    u, v = np.meshgrid(np.arange(m), np.arange(n), indexing="ij")
+    if closed:
+        a, b = 2 * np.pi * u / m, 2 * np.pi * v / n
+        V = np.stack([(0.62 + 0.2 * np.cos(b)) * np.cos(a), (0.62 + 0.2 * np.cos(b)) * np.sin(a), 0.2 * np.sin(b)], -1)
+    else:
+        x, y = u / (m - 1) - 0.5, v / (n - 1) - 0.5
+        V = np.stack([1.2 * x, 1.2 * y, 0.35 * np.cos(2.2 * x) * np.cos(1.7 * y) - 0.2], -1)
+    idx = lambda i, j: (i % m) * n + (j % n)  # noqa: E731
+    F = []
+    for i in range(m if closed else m - 1):
+        for j in range(n if closed else n - 1):
+            F.append((idx(i, j), idx(i + 1, j), idx(i + 1, j + 1)))
+            F.append((idx(i, j), idx(i + 1, j + 1), idx(i, j + 1)))
+    return np.ascontiguousarray(V.reshape(-1, 3), dtype=np.float32), np.asarray(F, dtype=np.int32)
+
+
+@pytest.mark.parametrize("schedule", ["cta", "cluster"])
+@pytest.mark.parametrize("closed", [True, False])
+def test_regular_and_open_meshes_six_word_rows(oracle, pd, closed, schedule):
+    """Sources whose vertices have at most 12 incident edges take the six-word instantiation of the loops; an open patch
+    adds rows that are padded early (the vertex itself: an exact zero term).  Same bits as the CPU loop."""
+    from meshode_b200 import engine
+    from meshode_b200.synth import synth_mesh
+    srcV, srcF = _grid_mesh(40, 31, closed)
+    assert np.bincount(srcF.reshape(-1)).max() == 6 and (np.bincount(srcF.reshape(-1)).min() == 6) == closed
+    tarV, tarF = synth_mesh(900, 5)
+    batch = engine.PairBatch([tuple(torch.from_numpy(a) for a in (srcV, srcF, tarV, tarF))], grid_resolution=32)
+    iters = 90
+    batch.deform(iters=iters, lr=1e-3, exact=True, schedule=schedule)
+    tmpl = oracle.Template(tarV, tarF, 32)
+    src_n = oracle.normalize_by_template(srcV, tmpl.scale, tmpl.trans)
+    ref, _ = oracle.rigid_adam(tmpl.grid, src_n, srcF, oracle.store_rigid(src_n, srcF), iters, 1e-3)
+    got = batch.V[0].cpu().numpy()
+    assert np.array_equal(got, ref), "max |dV| = %g" % np.abs(got - ref).max()
+    batch.release()
