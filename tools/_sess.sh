@@ -1,9 +1,11 @@
+# scratch session script for gpurun (edited per experiment): the final check of round 2
 set -u
 mkdir -p gpurun_out
-export MESHODE_EXACT=1 MESHODE_SCHEDULE=cta
-for rep in 1 2; do
-echo "== before"; MESHODE_B200_LIB=build/variants/libmeshode_noreuse3.so timeout 120 python tools/deform_bench.py 148 400 5000
-echo "== reuse3"; timeout 120 python tools/deform_bench.py 148 400 5000
-done
-unset MESHODE_EXACT MESHODE_SCHEDULE
-timeout 600 python -m pytest tests/test_gpu_deform.py -x -q 2>&1 | tail -5
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
+timeout 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/bench_n1.json'))
+print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['launch_ms'], d['roofline']['share_of_step'], d['cpu_baseline']['value'], d['clocks'])
+P
