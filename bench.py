@@ -583,8 +583,8 @@ def run_b200(a):
         alg = pair_iter_bytes(nV, nE) * a.iters * n
         ach = alg / (d_ms * 1e-3) / 1e9
         # DRAM traffic of this kernel per pair-iteration from the committed ncu --set full capture
-        # (profiles/r02_deform_v10.txt: 148 pairs x 300 iterations, dram read 0.625 GB + write 0.038 GB)
-        ncu_bytes_per_pair_iter = (0.624968e9 + 0.038425e9) / (148 * 300)
+        # (profiles/r02_deform_v12.txt: 148 pairs x 300 iterations, dram read 0.505 GB + write 0.028 GB)
+        ncu_bytes_per_pair_iter = (0.505264e9 + 0.027619e9) / (148 * 300)
         roof = {"kernel": "k_deform_adam_fused2 (+ k_deform_adam_cluster for the partial wave); rank 0: %d pairs x %d "
                           "iterations per step" % (n, a.iters),
                 "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
@@ -593,12 +593,12 @@ def run_b200(a):
                                 "%.0f kB per pair-iteration) scaled to this launch" % (ncu_bytes_per_pair_iter / 1e3),
                 "peak_source": hbm_src + " (sustained: timed inside a seconds-long step)",
                 "launch_ms": d_ms, "share_of_step": d_ms / ms_step,
-                "binding_resource": "L1/shared-memory data pipe: l1tex__data_pipe_lsu_wavefronts 84-86% of peak (ncu, "
-                                    "profiles/r02_deform_v10.txt), issue slots 62%",
+                "binding_resource": "L1/shared-memory data pipe: l1tex__data_pipe_lsu_wavefronts 84% of peak (ncu, "
+                                    "profiles/r02_deform_v12.txt), issue slots 70%",
                 "note": "algorithmic bytes = (28*V + 20*E + 72*V) per pair-iteration (SURVEY s8d) = %.3f MB; the kernel "
                         "keeps positions and rest positions in shared memory, corner records / tags / half of Adam's second "
                         "moment in tensor memory and the gradient in registers, so HBM is not its limiter (DRAM traffic is "
-                        "1.4%% of the algorithmic bytes) and the fraction can exceed 1: what bounds it is one random 128-bit + "
+                        "1.1%% of the algorithmic bytes) and the fraction can exceed 1: what bounds it is one random 128-bit + "
                         "one 64-bit shared-memory gather per neighbour (8.8 + 5.8 wavefronts per warp)" %
                         (pair_iter_bytes(nV, nE) / 1e6)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -1,11 +1,5 @@
-# scratch session script for gpurun (edited per experiment): the final check of round 2
 set -u
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
-timeout 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
-python - <<'P'
-import json
-d=json.load(open('gpurun_out/bench_n1.json'))
-print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['launch_ms'], d['roofline']['share_of_step'], d['cpu_baseline']['value'], d['clocks'])
-P
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_deform_adam -c 2 -f \
+    -o gpurun_out/prof_deform_v12 python tools/prof_target.py deform 157 300 > gpurun_out/ncu_deform_v12.log 2>&1
+tail -2 gpurun_out/ncu_deform_v12.log
