@@ -561,11 +561,6 @@ template <> struct Counters<false> {
   __device__ __forceinline__ void t64(unsigned) {}
 };
 
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 
 // per-lane view of the warp's state that the cluster routine needs.  Every warp owns a private slice of the CTA's
 // shared memory and never synchronises with the other warps of its CTA.
