@@ -1,7 +1,6 @@
-# scratch session script for gpurun (edited per experiment)
+# scratch session script for gpurun (edited per experiment): the final check of round 2
 set -u
 mkdir -p gpurun_out
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_sdf_tiles -s 1 -c 2 -f \
-    -o gpurun_out/prof_sdf64_v8 python tools/prof_target.py sdf64 > gpurun_out/ncu_sdf64_v8.log 2>&1
-tail -1 gpurun_out/ncu_sdf64_v8.log
-timeout 120 python tools/setup_bench.py 592 4 | tail -2
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
+timeout 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
